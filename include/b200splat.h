@@ -1,0 +1,187 @@
+/*
+ * b200splat.h -- C ABI of the B200-native (sm_100a) tile-based Gaussian-splatting rasterizer.
+ *
+ * This is the drop-in boundary for DepthSplat's rendering hot path.  The reference has NO native
+ * code of its own on this path: it binds the third-party pybind11 module
+ * `diff_gaussian_rasterization._C` (requirements.txt:23) through
+ *     src/model/decoder/cuda_splatting.py:98-123   GaussianRasterizationSettings + GaussianRasterizer(...)
+ *     src/model/decoder/cuda_splatting.py:191-216  same call, orthographic cameras
+ * once PER VIEW inside a Python loop (cuda_splatting.py:90), after replicating every Gaussian tensor
+ * per view (decoder_splatting_cuda.py:53-56).  The two entry points that module exports,
+ *     _C.rasterize_gaussians(bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier,
+ *                            cov3D_precomp, viewmatrix, projmatrix, tanfovx, tanfovy, H, W, sh, degree,
+ *                            campos, prefiltered, debug)
+ *     _C.rasterize_gaussians_backward(...)
+ * are replaced by b200s_forward_* / b200s_backward below, which take ALL views of ALL scenes of a
+ * batch in one call and read the un-replicated [B,N,...] Gaussian tensors directly.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller owns every buffer (inputs, outputs, the two workspaces); the library never
+ *     allocates, frees or synchronises; all work is enqueued on the `stream` argument
+ *     (a cudaStream_t passed as void*);
+ *   - re-entrant, no global state;
+ *   - return value: B200S_OK, or B200S_EBADARG (nothing enqueued), or B200S_ECUDA (a launch failed;
+ *     `b200s_last_cuda_error` holds the code).  Capacity overflow of the (tile,depth) pair buffers
+ *     is NOT a return code: it is reported in the device status block (B200sStatus) so that the
+ *     happy path needs no host synchronisation; the host reads it when it chooses to.
+ */
+#ifndef B200SPLAT_H
+#define B200SPLAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200S_ABI_VERSION 1
+
+enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
+
+/* Gaussian tensor layouts accepted directly (no transposition copies on the caller's side). */
+enum { B200S_COV_3X3 = 0 /* [B,N,3,3] DepthSplat Gaussians.covariances */, B200S_COV_UPPER6 = 1 /* [B,N,6] extension cov3D_precomp */ };
+enum { B200S_SH_CHANNEL_MAJOR = 0 /* [B,N,3,d_sh] DepthSplat Gaussians.harmonics */, B200S_SH_COEFF_MAJOR = 1 /* [B,N,d_sh,3] extension shs */ };
+/* depth channel composited next to RGB: colour = f(z_cam) per render_depth_cuda (cuda_splatting.py:238-246) */
+enum { B200S_DEPTH_NONE = 0, B200S_DEPTH_Z = 1 /* "depth", "relative_disparity" */, B200S_DEPTH_DISPARITY = 2, B200S_DEPTH_LOG = 3 };
+
+/* The scene batch: B scenes of N Gaussians each, fp32, contiguous. */
+typedef struct B200sScene {
+  int32_t num_scenes;     /* B */
+  int32_t num_gaussians;  /* N per scene */
+  int32_t sh_degree;      /* 0..3 active degree; ignored when colors_precomp != NULL */
+  int32_t sh_coeffs;      /* d_sh = coefficients stored per channel (>= (sh_degree+1)^2) */
+  int32_t cov_layout;     /* B200S_COV_* */
+  int32_t sh_layout;      /* B200S_SH_* */
+  const float* means;          /* [B,N,3] */
+  const float* covariances;    /* [B,N,3,3] or [B,N,6] */
+  const float* harmonics;      /* [B,N,3,d_sh] or [B,N,d_sh,3]; NULL when colors_precomp is used */
+  const float* colors_precomp; /* [B,N,3] or NULL (use_sh=False path, cuda_splatting.py:117) */
+  const float* opacities;      /* [B,N] */
+} B200sScene;
+
+/* The views: VV = total number of (scene, target camera) pairs rendered by this call. */
+typedef struct B200sViews {
+  int32_t num_views;      /* VV */
+  int32_t height, width;  /* H, W (all views of a call share the image size) */
+  int32_t depth_mode;     /* B200S_DEPTH_* */
+  const int32_t* scene_index; /* [VV] scene of each view */
+  const float* viewmatrix;    /* [VV,16] world->camera, transposed storage (cuda_splatting.py:85) */
+  const float* projmatrix;    /* [VV,16] full projection, transposed storage (cuda_splatting.py:86) */
+  const float* campos;        /* [VV,3] */
+  const float* tanfov;        /* [VV,2] (tanfovx, tanfovy) */
+  const float* background;    /* [VV,3] */
+  const float* scale;         /* [VV,2] (s, s*s): means*s and cov*s^2 are applied in-kernel (scale_invariant,
+                                 cuda_splatting.py:63-70); NULL => 1 */
+  const float* depth_affine;  /* [VV,4] row 2 of the UNnormalised world->camera matrix, z_cam = r.m + t
+                                 (cuda_splatting.py:238-241); required when depth_mode != NONE */
+  const float* depth_clamp;   /* [VV,2] (near, far) for B200S_DEPTH_LOG; may be NULL otherwise */
+} B200sViews;
+
+/* Problem dimensions -> workspace plan. */
+typedef struct B200sDims {
+  int32_t num_scenes, num_gaussians, num_views, height, width;
+  int64_t pair_capacity; /* R_cap: capacity of the (key,value) pair buffers, < 2^32 */
+} B200sDims;
+
+/* Byte offsets of every region inside the two caller-owned workspaces.
+ * `saved` must stay alive from forward to backward; `scratch` may be reused right after forward. */
+typedef struct B200sPlan {
+  int32_t abi_version;
+  int32_t tile_bits, view_bits, sort_bits, sort_passes;
+  int32_t grid_x, grid_y, tiles, bins; /* bins = num_views << tile_bits */
+  int32_t pre_tickets;                 /* blocks of the preprocess kernel */
+  int32_t sort_tiles_cap;              /* onesweep tiles at full capacity */
+  int32_t final_in_a;                  /* 1 if the sorted values end in saved.vals_a (always 1) */
+  int64_t pair_capacity;
+  /* saved workspace */
+  size_t saved_bytes;
+  size_t off_status;     /* B200sStatus */
+  size_t off_rec;        /* [VV,N] 64-byte projected records */
+  size_t off_vals_a;     /* [R_cap] u32 : sorted Gaussian indices after forward */
+  size_t off_ranges;     /* [bins] uint2 (start,end) into vals_a */
+  size_t off_final_T;    /* [VV,H,W] f32 */
+  size_t off_n_contrib;  /* [VV,H,W] u32 */
+  /* scratch workspace */
+  size_t scratch_bytes;
+  size_t off_keys_a, off_keys_b; /* [R_cap] u64 each */
+  size_t off_vals_b;             /* [R_cap] u32 */
+  size_t off_scan_state;         /* [pre_tickets] u64 decoupled look-back words */
+  size_t off_hist;               /* [8,256] u32 digit histograms -> exclusive bases */
+  size_t off_lookback;           /* [2, sort_tiles_cap, 256] u32 onesweep look-back words */
+  size_t off_counters;           /* [64] u32 ticket / tile counters */
+  size_t off_grad_rec;           /* backward only: [VV,N] 48-byte gradient records (may alias keys) */
+} B200sPlan;
+
+/* Device status block (first bytes of the saved workspace). */
+typedef struct B200sStatus {
+  uint64_t num_pairs;     /* R: total (tile,Gaussian) pairs over all views of the call */
+  uint32_t overflow;      /* 1 if R > pair_capacity: nothing downstream of duplication ran */
+  uint32_t num_visible;   /* Gaussian-view pairs that survived culling (Nv summed over views) */
+  uint64_t tested;        /* optional flop accounting (filled when B200sOut.count_work != 0) */
+  uint64_t blended;
+  uint32_t max_tile_len;  /* longest per-tile list */
+  uint32_t reserved[5];
+} B200sStatus;
+
+typedef struct B200sOut {
+  float* color;      /* [VV,3,H,W] */
+  float* depth;      /* [VV,H,W] or NULL (required when depth_mode != NONE) */
+  int32_t* radii;    /* [VV,N] or NULL */
+  int32_t count_work;/* != 0: accumulate tested/blended/max_tile_len into the status block */
+} B200sOut;
+
+typedef struct B200sGradOut { /* upstream gradients */
+  const float* dL_dcolor; /* [VV,3,H,W] */
+  const float* dL_ddepth; /* [VV,H,W] or NULL */
+} B200sGradOut;
+
+typedef struct B200sGradIn { /* all fp32, OVERWRITTEN (summed over the views of each scene) */
+  float* dL_dmeans;       /* [B,N,3] */
+  float* dL_dcovariances; /* same layout as B200sScene.covariances; lower triangle of 3x3 gets 0 */
+  float* dL_dharmonics;   /* same layout as B200sScene.harmonics, or NULL */
+  float* dL_dcolors;      /* [B,N,3] when colors_precomp was used, or NULL */
+  float* dL_dopacities;   /* [B,N] */
+  float* dL_dmeans2D;     /* [VV,N,3] screen-space mean gradients (extension API parity), or NULL */
+} B200sGradIn;
+
+/* Pure host function: fills the plan for the given dimensions.  No CUDA calls. */
+int b200s_plan(const B200sDims* dims, B200sPlan* plan);
+
+/* Stage A of forward: preprocess (cull, EWA projection, SH->RGB, tile rects) fused with the
+ * tile-count scan and the emission of 64-bit (view|tile|depth) keys.  Writes B200sStatus
+ * (num_pairs, overflow, num_visible).  Replaces preprocessCUDA + InclusiveSum + duplicateWithKeys
+ * behind _C.rasterize_gaussians. */
+int b200s_forward_bin(const B200sScene* scene, const B200sViews* views, const B200sPlan* plan, void* saved,
+                      void* scratch, const B200sOut* out, void* stream);
+
+/* Stage B of forward: onesweep radix sort of the pairs, tile ranges, 16x16-tile compositing of
+ * colour (+ depth).  A no-op if the status block says overflow.  Replaces SortPairs +
+ * identifyTileRanges + renderCUDA behind _C.rasterize_gaussians. */
+int b200s_forward_render(const B200sScene* scene, const B200sViews* views, const B200sPlan* plan, void* saved,
+                         void* scratch, const B200sOut* out, void* stream);
+
+/* Backward: reverse-traversal compositing backward (warp-reduced gradients, one atomic per
+ * gradient component per warp) followed by the preprocess backward that sums over the views of
+ * each scene.  Replaces _C.rasterize_gaussians_backward AND the autograd of the per-view
+ * replication (decoder_splatting_cuda.py:53-56). */
+int b200s_backward(const B200sScene* scene, const B200sViews* views, const B200sPlan* plan, const void* saved,
+                   void* scratch, const B200sOut* fwd_out, const B200sGradOut* gout, const B200sGradIn* gin, void* stream);
+
+/* Stand-alone stable LSD radix sort of (u64 key, u32 value) pairs on the low `bits` bits -- the
+ * same onesweep kernels forward uses, exported for the parity tests and the sort micro-benchmark.
+ * keys_a/vals_a hold the input; the sorted output ends in keys_a/vals_a.  `tmp` needs
+ * b200s_sort_tmp_bytes(n) bytes. */
+size_t b200s_sort_tmp_bytes(int64_t n);
+int b200s_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, int32_t bits,
+                     void* tmp, void* stream);
+
+int b200s_abi_version(void);
+int b200s_last_cuda_error(void);       /* cudaError_t of the last failed launch on this thread */
+const char* b200s_build_info(void);    /* "sm_100a nvcc <ver> ..." */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPLAT_H */

@@ -1,0 +1,201 @@
+// api.cu -- the extern "C" boundary declared in include/b200splat.h.  Host code only: argument
+// checks, the workspace plan, and kernel launches on the caller's stream.  No allocation, no
+// synchronisation, no global state (one thread-local error slot).
+#include <stdio.h>
+#include <string.h>
+
+#include "kernels.cuh"
+
+
+using namespace b200s;
+
+static thread_local int g_last_cuda_error = 0;
+
+static int fail(cudaError_t e) {
+  g_last_cuda_error = (int)e;
+  return B200S_ECUDA;
+}
+static int sm_count() {
+  static thread_local int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static int bits_for(int n) { int b = 0; while ((1 << b) < n) b++; return b; }
+
+extern "C" {
+
+int b200s_abi_version(void) { return B200S_ABI_VERSION; }
+int b200s_last_cuda_error(void) { return g_last_cuda_error; }
+const char* b200s_build_info(void) {
+#define B200S_STR2(x) #x
+#define B200S_STR(x) B200S_STR2(x)
+  return "b200splat abi " B200S_STR(B200S_ABI_VERSION) " sm_100a nvcc " B200S_STR(__CUDACC_VER_MAJOR__) "." B200S_STR(__CUDACC_VER_MINOR__);
+}
+
+int b200s_plan(const B200sDims* d, B200sPlan* p) {
+  if (!d || !p) return B200S_EBADARG;
+  if (d->num_scenes <= 0 || d->num_gaussians <= 0 || d->num_views <= 0 || d->height <= 0 || d->width <= 0) return B200S_EBADARG;
+  if (d->pair_capacity <= 0) return B200S_EBADARG;
+  memset(p, 0, sizeof(*p));
+  p->abi_version = B200S_ABI_VERSION;
+  p->grid_x = (d->width + TILE_X - 1) / TILE_X;
+  p->grid_y = (d->height + TILE_Y - 1) / TILE_Y;
+  if (p->grid_x > 255 || p->grid_y > 255) return B200S_EBADARG;  // rect packing in the record
+  p->tiles = p->grid_x * p->grid_y;
+  p->tile_bits = bits_for(p->tiles);
+  p->view_bits = bits_for(d->num_views);
+  p->bins = d->num_views << p->tile_bits;
+  p->sort_bits = 32 + p->tile_bits + p->view_bits;
+  p->sort_passes = (p->sort_bits + 7) / 8;
+  if (p->sort_passes > 8) return B200S_EBADARG;
+  // the onesweep look-back word holds a 30-bit running count
+  if (d->pair_capacity >= (1ll << 30)) return B200S_EBADARG;
+  const long long chunks = (d->num_gaussians + PRE_THREADS - 1) / PRE_THREADS;
+  if (chunks * d->num_views > 0x7fffffffll) return B200S_EBADARG;
+  p->pre_tickets = (int)(chunks * d->num_views);
+  p->sort_tiles_cap = sort_tiles_for(d->pair_capacity);
+  p->final_in_a = 1;
+  p->pair_capacity = d->pair_capacity;
+  const size_t VN = (size_t)d->num_views * d->num_gaussians;
+  const size_t VP = (size_t)d->num_views * d->height * d->width;
+  const size_t R = (size_t)d->pair_capacity;
+  size_t o = 0;
+  p->off_status = o; o = align_up(o + sizeof(B200sStatus));
+  p->off_rec = o; o = align_up(o + VN * sizeof(Rec));
+  p->off_vals_a = o; o = align_up(o + R * 4);
+  p->off_ranges = o; o = align_up(o + (size_t)p->bins * 8);
+  p->off_final_T = o; o = align_up(o + VP * 4);
+  p->off_n_contrib = o; o = align_up(o + VP * 4);
+  p->saved_bytes = o;
+  o = 0;
+  p->off_keys_a = o; o = align_up(o + R * 8);
+  p->off_keys_b = o; o = align_up(o + R * 8);
+  p->off_vals_b = o; o = align_up(o + R * 4);
+  p->off_scan_state = o; o = align_up(o + (size_t)p->pre_tickets * 8);
+  p->off_hist = o; o = align_up(o + 8 * 256 * 4);
+  p->off_lookback = o; o = align_up(o + 2 * (size_t)p->sort_tiles_cap * 256 * 4);
+  p->off_counters = o; o = align_up(o + CNT_WORDS * 4);
+  const size_t fwd_bytes = o;
+  p->off_grad_rec = 0;  // backward reuses the scratch from its start (keys are dead by then)
+  const size_t bwd_bytes = align_up(VN * GREC_FLOATS * 4);
+  p->scratch_bytes = fwd_bytes > bwd_bytes ? fwd_bytes : bwd_bytes;
+  return B200S_OK;
+}
+
+static int check_common(const B200sScene* sc, const B200sViews* vw, const B200sPlan* pl, const void* saved, const void* scratch) {
+  if (!sc || !vw || !pl || !saved || !scratch) return B200S_EBADARG;
+  if (pl->abi_version != B200S_ABI_VERSION) return B200S_EBADARG;
+  if (!sc->means || !sc->covariances || !sc->opacities) return B200S_EBADARG;
+  if (!sc->harmonics && !sc->colors_precomp) return B200S_EBADARG;
+  if (!sc->colors_precomp) {
+    if (sc->sh_degree < 0 || sc->sh_degree > 3) return B200S_EBADARG;
+    if (sc->sh_coeffs < (sc->sh_degree + 1) * (sc->sh_degree + 1) || sc->sh_coeffs > 16) return B200S_EBADARG;
+  }
+  if (!vw->scene_index || !vw->viewmatrix || !vw->projmatrix || !vw->campos || !vw->tanfov || !vw->background) return B200S_EBADARG;
+  if (vw->depth_mode != B200S_DEPTH_NONE && !vw->depth_affine) return B200S_EBADARG;
+  if (vw->depth_mode == B200S_DEPTH_LOG && !vw->depth_clamp) return B200S_EBADARG;
+  if (vw->depth_mode < 0 || vw->depth_mode > 3) return B200S_EBADARG;
+  if ((vw->width + TILE_X - 1) / TILE_X != pl->grid_x || (vw->height + TILE_Y - 1) / TILE_Y != pl->grid_y) return B200S_EBADARG;
+  if (((long long)((sc->num_gaussians + PRE_THREADS - 1) / PRE_THREADS)) * vw->num_views != pl->pre_tickets) return B200S_EBADARG;
+  if ((vw->num_views << pl->tile_bits) != pl->bins) return B200S_EBADARG;
+  return B200S_OK;
+}
+
+int b200s_forward_bin(const B200sScene* sc, const B200sViews* vw, const B200sPlan* pl, void* saved, void* scratch, const B200sOut* out,
+                      void* stream) {
+  const int rc = check_common(sc, vw, pl, saved, scratch);
+  if (rc != B200S_OK) return rc;
+  const cudaError_t e = launch_preprocess_bin(*sc, *vw, *pl, (char*)saved, (char*)scratch, out, (cudaStream_t)stream);
+  return e == cudaSuccess ? B200S_OK : fail(e);
+}
+
+int b200s_forward_render(const B200sScene* sc, const B200sViews* vw, const B200sPlan* pl, void* saved_, void* scratch_, const B200sOut* out,
+                         void* stream_) {
+  const int rc = check_common(sc, vw, pl, saved_, scratch_);
+  if (rc != B200S_OK) return rc;
+  if (!out || !out->color) return B200S_EBADARG;
+  if (vw->depth_mode != B200S_DEPTH_NONE && !out->depth) return B200S_EBADARG;
+  char* saved = (char*)saved_; char* scratch = (char*)scratch_;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200sStatus* st = reinterpret_cast<B200sStatus*>(saved + pl->off_status);
+  CountRef cnt{reinterpret_cast<const unsigned long long*>(&st->num_pairs), &st->overflow, 0ull};
+  uint64_t* keys_a = reinterpret_cast<uint64_t*>(scratch + pl->off_keys_a);
+  uint64_t* keys_b = reinterpret_cast<uint64_t*>(scratch + pl->off_keys_b);
+  uint32_t* vals_a = reinterpret_cast<uint32_t*>(saved + pl->off_vals_a);
+  uint32_t* vals_b = reinterpret_cast<uint32_t*>(scratch + pl->off_vals_b);
+  cudaError_t e = launch_sort(keys_a, vals_a, keys_b, vals_b, pl->sort_passes, pl->pair_capacity, cnt, reinterpret_cast<uint32_t*>(scratch + pl->off_hist),
+                              reinterpret_cast<uint32_t*>(scratch + pl->off_lookback), reinterpret_cast<uint32_t*>(scratch + pl->off_counters), sm_count(), stream);
+  if (e != cudaSuccess) return fail(e);
+  uint2* ranges = reinterpret_cast<uint2*>(saved + pl->off_ranges);
+  e = launch_tile_ranges(keys_a, cnt, ranges, pl->bins, pl->pair_capacity, sm_count(), stream);
+  if (e != cudaSuccess) return fail(e);
+  CompArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = sc->num_gaussians; a.H = vw->height; a.W = vw->width; a.grid_x = pl->grid_x; a.tile_bits = pl->tile_bits;
+  a.rec = reinterpret_cast<const Rec*>(saved + pl->off_rec);
+  a.vals = vals_a; a.ranges = ranges; a.bg = vw->background; a.overflow = &st->overflow;
+  a.color = out->color; a.depth = out->depth;
+  a.final_T = reinterpret_cast<float*>(saved + pl->off_final_T);
+  a.n_contrib = reinterpret_cast<uint32_t*>(saved + pl->off_n_contrib);
+  a.status = st;
+  e = launch_composite_fwd(a, pl->tiles, vw->num_views, vw->depth_mode != B200S_DEPTH_NONE, out->count_work != 0, stream);
+  return e == cudaSuccess ? B200S_OK : fail(e);
+}
+
+int b200s_backward(const B200sScene* sc, const B200sViews* vw, const B200sPlan* pl, const void* saved_, void* scratch_, const B200sOut* fwd_out,
+                   const B200sGradOut* gout, const B200sGradIn* gin, void* stream_) {
+  const int rc = check_common(sc, vw, pl, saved_, scratch_);
+  if (rc != B200S_OK) return rc;
+  if (!gout || !gin || !gout->dL_dcolor || !gin->dL_dmeans || !gin->dL_dcovariances || !gin->dL_dopacities) return B200S_EBADARG;
+  if (vw->depth_mode != B200S_DEPTH_NONE && !gout->dL_ddepth) return B200S_EBADARG;
+  if (sc->colors_precomp ? !gin->dL_dcolors : !gin->dL_dharmonics) return B200S_EBADARG;
+  (void)fwd_out;
+  const char* saved = (const char*)saved_; char* scratch = (char*)scratch_;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const B200sStatus* st = reinterpret_cast<const B200sStatus*>(saved + pl->off_status);
+  float* grad_rec = reinterpret_cast<float*>(scratch + pl->off_grad_rec);
+  cudaError_t e = cudaMemsetAsync(grad_rec, 0, (size_t)vw->num_views * sc->num_gaussians * GREC_FLOATS * sizeof(float), stream);
+  if (e != cudaSuccess) return fail(e);
+  CompArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = sc->num_gaussians; a.H = vw->height; a.W = vw->width; a.grid_x = pl->grid_x; a.tile_bits = pl->tile_bits;
+  a.rec = reinterpret_cast<const Rec*>(saved + pl->off_rec);
+  a.vals = reinterpret_cast<const uint32_t*>(saved + pl->off_vals_a);
+  a.ranges = reinterpret_cast<const uint2*>(saved + pl->off_ranges);
+  a.bg = vw->background; a.overflow = &st->overflow;
+  a.final_T = const_cast<float*>(reinterpret_cast<const float*>(saved + pl->off_final_T));
+  a.n_contrib = const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(saved + pl->off_n_contrib));
+  a.dL_dcolor = gout->dL_dcolor; a.dL_ddepth = gout->dL_ddepth; a.grad_rec = grad_rec;
+  e = launch_composite_bwd(a, pl->tiles, vw->num_views, vw->depth_mode != B200S_DEPTH_NONE, stream);
+  if (e != cudaSuccess) return fail(e);
+  e = launch_preprocess_bwd(*sc, *vw, *pl, saved, scratch, *gin, stream);
+  return e == cudaSuccess ? B200S_OK : fail(e);
+}
+
+size_t b200s_sort_tmp_bytes(int64_t n) { return sort_tmp_bytes(n); }
+
+int b200s_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, int32_t bits, void* tmp, void* stream) {
+  if (!keys_a || !vals_a || !keys_b || !vals_b || !tmp || n < 0 || bits <= 0 || bits > 64 || n >= (1ll << 30)) return B200S_EBADARG;
+  if (n == 0) return B200S_OK;
+  const int passes = (bits + 7) / 8;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(tmp);
+  uint32_t* lookback = hist + 8 * 256;
+  uint32_t* counters = lookback + 2 * (size_t)sort_tiles_for(n) * 256;
+  // the stand-alone entry point takes its input in A: an odd pass count needs it in B first
+  cudaStream_t s = (cudaStream_t)stream;
+  if (passes % 2) {
+    cudaError_t e = cudaMemcpyAsync(keys_b, keys_a, (size_t)n * 8, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return fail(e);
+    e = cudaMemcpyAsync(vals_b, vals_a, (size_t)n * 4, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return fail(e);
+  }
+  CountRef cnt{nullptr, nullptr, (unsigned long long)n};
+  const cudaError_t e = launch_sort(keys_a, vals_a, keys_b, vals_b, passes, n, cnt, hist, lookback, counters, sm_count(), s);
+  return e == cudaSuccess ? B200S_OK : fail(e);
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+// preprocess.cu -- stage A of forward: ONE kernel that replaces the extension's preprocessCUDA,
+// cub::DeviceScan::InclusiveSum (+ its blocking D2H read) and duplicateWithKeys:
+//
+//   ticket (dynamic block id, view-fastest so that the blocks that read the same 256 Gaussians for
+//   different views run together and share them through L2)
+//     -> coalesced float4 staging of the Gaussian chunk (means, covariances, SH, opacities) into
+//        shared memory in the caller's own tensor layouts (no transposition copies)
+//     -> per thread: cull, projection, EWA cov2D, conic, radius, tile rect, SH->RGB, depth colour
+//     -> 64-byte projected records written back coalesced through shared memory
+//     -> block scan of tiles_touched + single-pass decoupled look-back across tickets
+//     -> emission of 64-bit (view | tile | depth-bits) keys and Gaussian-index values at the scanned
+//        offsets: per thread for small rects, one warp per large-rect Gaussian otherwise.
+//
+// HBM-bound: per (view, Gaussian) 148 B read (L2-shared across views) + 64 B record + 12 B per pair.
+#include "kernels.cuh"
+
+namespace b200s {
+
+struct PreArgs {
+  int N, VV, H, W, grid_x, grid_y, tile_bits, chunks, n_tickets;
+  unsigned long long pair_capacity;
+  int fpg;          // floats per Gaussian staged: 3 + cov + colour + 1
+  int cov_floats;   // 9 or 6
+  int col_floats;   // 3*d_sh or 3
+  int col_stride;   // padded to odd
+  Rec* rec;
+  uint64_t* keys;
+  uint32_t* vals;
+  uint64_t* scan_state;
+  uint32_t* counters;
+  B200sStatus* status;
+  int32_t* radii;
+};
+
+constexpr uint64_t SCAN_FLAG_AGG = 1ull << 62, SCAN_FLAG_PREFIX = 2ull << 62, SCAN_VALUE_MASK = (1ull << 62) - 1;
+constexpr int WARP_EMIT_THRESHOLD = 12;
+
+// cooperative global -> shared copy of `count` floats; float4 path when both sides are 16B aligned
+__device__ __forceinline__ void stage_in(float* dst, const float* __restrict__ src, int count) {
+  const int tid = threadIdx.x;
+  if ((((uintptr_t)src) & 15) == 0 && (count & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = tid; i < (count >> 2); i += PRE_THREADS) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = tid; i < count; i += PRE_THREADS) dst[i] = __ldg(src + i);
+  }
+}
+// same, into rows padded from k to `stride` floats
+__device__ __forceinline__ void stage_in_padded(float* dst, const float* __restrict__ src, int count, int k, int stride) {
+  if (k == stride) { stage_in(dst, src, count); return; }
+  for (int i = threadIdx.x; i < count; i += PRE_THREADS) { const int g = i / k; dst[g * stride + (i - g * k)] = __ldg(src + i); }
+}
+
+__device__ __forceinline__ float eval_sh_channel(int deg, const float* sh, int kstride, float x, float y, float z) {
+#define S(k) sh[(k) * kstride]
+  float r = SH_C0 * S(0);
+  if (deg > 0) {
+    r = r - SH_C1 * y * S(1) + SH_C1 * z * S(2) - SH_C1 * x * S(3);
+    if (deg > 1) {
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      r = r + SH_C2[0] * xy * S(4) + SH_C2[1] * yz * S(5) + SH_C2[2] * (2.0f * zz - xx - yy) * S(6) +
+          SH_C2[3] * xz * S(7) + SH_C2[4] * (xx - yy) * S(8);
+      if (deg > 2) {
+        r = r + SH_C3[0] * y * (3.0f * xx - yy) * S(9) + SH_C3[1] * xy * z * S(10) +
+            SH_C3[2] * y * (4.0f * zz - xx - yy) * S(11) + SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * S(12) +
+            SH_C3[4] * x * (4.0f * zz - xx - yy) * S(13) + SH_C3[5] * z * (xx - yy) * S(14) +
+            SH_C3[6] * x * (xx - 3.0f * yy) * S(15);
+      }
+    }
+  }
+#undef S
+  return r;
+}
+
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_bin_kernel(const B200sScene sc, const B200sViews vw, const PreArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ ViewParams vp;
+  __shared__ int s_ticket;
+  __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
+  __shared__ unsigned long long s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_ticket = (int)atomicAdd(&a.counters[CNT_PRE_TICKET], 1u);
+  __syncthreads();
+  const int ticket = s_ticket;
+  if (ticket >= a.n_tickets) return;
+  const int view = ticket % a.VV, chunk = ticket / a.VV;
+  if (tid == 0) load_view_params(vp, vw, view, a.H, a.W);
+  __syncthreads();
+  const int scene = vp.scene;
+  const int i0 = chunk * PRE_THREADS;
+  const int n = min(PRE_THREADS, a.N - i0);
+  const long long g0 = (long long)scene * a.N + i0;
+
+  // ---- stage the Gaussian chunk --------------------------------------------------------------
+  float* s_mean = smem;                                  // [256*3]
+  float* s_cov = s_mean + PRE_THREADS * 3;               // [256*cov_floats]
+  float* s_op = s_cov + PRE_THREADS * a.cov_floats;      // [256]
+  float* s_col = s_op + PRE_THREADS;                     // [256*col_stride]
+  stage_in(s_mean, sc.means + g0 * 3, n * 3);
+  stage_in(s_cov, sc.covariances + g0 * a.cov_floats, n * a.cov_floats);
+  stage_in(s_op, sc.opacities + g0, n);
+  const float* col_src = sc.colors_precomp ? sc.colors_precomp : sc.harmonics;
+  stage_in_padded(s_col, col_src + g0 * a.col_floats, n * a.col_floats, a.col_floats, a.col_stride);
+  __syncthreads();
+
+  // ---- per-Gaussian projection ---------------------------------------------------------------
+  Rec out;
+  out.q0 = make_float4(0.f, 0.f, 0.f, 0.f); out.q1 = out.q0; out.q2 = make_float4(0.f, 0.f, -1.f, -1.f); out.q3 = out.q0;
+  uint32_t tiles = 0;
+  int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
+  float depth = 0.f;
+  if (tid < n) {
+    const float mraw[3] = {s_mean[tid * 3], s_mean[tid * 3 + 1], s_mean[tid * 3 + 2]};
+    const float m[3] = {__fmul_rn(mraw[0], vp.s), __fmul_rn(mraw[1], vp.s), __fmul_rn(mraw[2], vp.s)};
+    const float phx = xform_row(vp.proj, 0, m[0], m[1], m[2]);
+    const float phy = xform_row(vp.proj, 1, m[0], m[1], m[2]);
+    const float phw = xform_row(vp.proj, 3, m[0], m[1], m[2]);
+    const float pw = __frcp_rn(__fadd_rn(phw, 0.0000001f));
+    const float ppx = __fmul_rn(phx, pw), ppy = __fmul_rn(phy, pw);
+    const float pvz = xform_row(vp.view, 2, m[0], m[1], m[2]);
+    if (pvz > NEAR_CULL) {
+      float c6[6];
+      const float* cp = s_cov + tid * a.cov_floats;
+      if (a.cov_floats == 6) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) c6[k] = __fmul_rn(cp[k], vp.s2);
+      } else {
+        c6[0] = __fmul_rn(cp[0], vp.s2); c6[1] = __fmul_rn(cp[1], vp.s2); c6[2] = __fmul_rn(cp[2], vp.s2);
+        c6[3] = __fmul_rn(cp[4], vp.s2); c6[4] = __fmul_rn(cp[5], vp.s2); c6[5] = __fmul_rn(cp[8], vp.s2);
+      }
+      Cov2D q;
+      compute_cov2d(m, c6, vp, q);
+      const float det = __fsub_rn(__fmul_rn(q.a, q.c), __fmul_rn(q.b, q.b));
+      if (det != 0.0f) {
+        const float det_inv = __frcp_rn(det);
+        const float mid = __fmul_rn(0.5f, __fadd_rn(q.a, q.c));
+        const float disc = __fsqrt_rn(fmaxf(LAMBDA_FLOOR, __fsub_rn(__fmul_rn(mid, mid), det)));
+        const float lam = fmaxf(__fadd_rn(mid, disc), __fsub_rn(mid, disc));
+        const float radf = ceilf(__fmul_rn(3.f, __fsqrt_rn(lam)));
+        const int radius = (int)radf;
+        const float px = ndc2pix(ppx, a.W), py = ndc2pix(ppy, a.H);
+        get_rect(px, py, radius, a.grid_x, a.grid_y, rx0, ry0, rx1, ry1);
+        tiles = (uint32_t)((rx1 - rx0) * (ry1 - ry0));
+        if (tiles > 0) {
+          depth = pvz;
+          const float opac = s_op[tid];
+          float rgb[3];
+          uint32_t flags = 0;
+          const float* cs = s_col + tid * a.col_stride;
+          if (sc.colors_precomp) {
+            rgb[0] = cs[0]; rgb[1] = cs[1]; rgb[2] = cs[2];
+          } else {
+            float dx = m[0] - vp.campos[0], dy = m[1] - vp.campos[1], dz = m[2] - vp.campos[2];
+            const float len = __fsqrt_rn(dot3c(dx, dx, dy, dy, dz, dz));
+            dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
+            const int cstride = (sc.sh_layout == B200S_SH_CHANNEL_MAJOR) ? sc.sh_coeffs : 1;
+            const int kstride = (sc.sh_layout == B200S_SH_CHANNEL_MAJOR) ? 1 : 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+              float r = eval_sh_channel(sc.sh_degree, cs + ch * cstride, kstride, dx, dy, dz) + 0.5f;
+              if (r < 0.f) flags |= (1u << ch);
+              rgb[ch] = fmaxf(r, 0.f);
+            }
+          }
+          float zc = 0.f;
+          if (vw.depth_mode != B200S_DEPTH_NONE) {
+            const float z = __fadd_rn(__fmaf_rn(vp.daff[2], mraw[2], __fmaf_rn(vp.daff[0], mraw[0], __fmul_rn(vp.daff[1], mraw[1]))), vp.daff[3]);
+            if (vw.depth_mode == B200S_DEPTH_Z) zc = z;
+            else if (vw.depth_mode == B200S_DEPTH_DISPARITY) zc = __frcp_rn(z);
+            else zc = logf(fmaxf(fminf(z, vp.dnear), vp.dfar));
+          }
+          // conservative half-extents of the region where alpha can reach 1/255
+          float ex = -1.f, ey = -1.f;
+          const float o255 = 255.0f * opac;
+          if (o255 >= 1.0f) {
+            const float tau2 = 2.0f * logf(o255);
+            ex = sqrtf(tau2 * q.a) * 1.01f + 0.1f;
+            ey = sqrtf(tau2 * q.c) * 1.01f + 0.1f;
+          }
+          out.q0 = make_float4(px, py, __fmul_rn(q.c, det_inv), __fmul_rn(-q.b, det_inv));
+          out.q1 = make_float4(__fmul_rn(q.a, det_inv), opac, rgb[0], rgb[1]);
+          out.q2 = make_float4(rgb[2], zc, ex, ey);
+          const uint32_t rect = (uint32_t)rx0 | ((uint32_t)ry0 << 8) | ((uint32_t)rx1 << 16) | ((uint32_t)ry1 << 24);
+          out.q3 = make_float4(depth, __int_as_float(radius), __uint_as_float(rect), __uint_as_float(flags));
+        }
+      }
+    }
+    if (a.radii) a.radii[(long long)view * a.N + i0 + tid] = tiles > 0 ? __float_as_int(out.q3.y) : 0;
+  }
+
+  // ---- records out, coalesced through shared memory -------------------------------------------
+  __syncthreads();  // everyone is done reading the staged inputs
+  {
+    float4* s_rec = reinterpret_cast<float4*>(smem);  // [256*4]
+    s_rec[tid * 4 + 0] = out.q0; s_rec[tid * 4 + 1] = out.q1; s_rec[tid * 4 + 2] = out.q2; s_rec[tid * 4 + 3] = out.q3;
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(a.rec + (long long)view * a.N + i0);
+    for (int i = tid; i < n * 4; i += PRE_THREADS) dst[i] = s_rec[i];
+  }
+
+  // ---- block scan of tiles_touched -----------------------------------------------------------
+  uint32_t incl = tiles;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) s_warp_tot[warp] = incl;
+  const uint32_t vis_mask = __ballot_sync(0xffffffffu, tiles > 0);
+  __syncthreads();
+  uint32_t warp_excl = 0, block_total = 0;
+#pragma unroll
+  for (int w = 0; w < PRE_THREADS / 32; w++) { const uint32_t t = s_warp_tot[w]; if (w < warp) warp_excl += t; block_total += t; }
+  const uint32_t my_excl = warp_excl + incl - tiles;
+  if (lane == 0 && vis_mask) atomicAdd(&a.status->num_visible, (uint32_t)__popc(vis_mask));
+
+  // ---- decoupled look-back over tickets (warp 0) ------------------------------------------------
+  if (warp == 0) {
+    if (lane == 0) st_volatile_u64(&a.scan_state[ticket], (ticket == 0 ? SCAN_FLAG_PREFIX : SCAN_FLAG_AGG) | (uint64_t)block_total);
+    unsigned long long excl = 0;
+    int idx = ticket - 1;  // window covers [idx-31, idx]
+    while (idx >= 0) {
+      const int t = idx - lane;
+      uint64_t w = SCAN_FLAG_PREFIX;  // tickets < 0 count as an empty prefix
+      if (t >= 0) { do { w = ld_volatile_u64(&a.scan_state[t]); } while ((w >> 62) == 0); }
+      const uint32_t pmask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+      const int first = pmask ? (__ffs(pmask) - 1) : 32;
+      unsigned long long v = (lane <= first) ? (w & SCAN_VALUE_MASK) : 0ull;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      excl += v;
+      if (pmask) break;
+      idx -= 32;
+    }
+    if (lane == 0) {
+      if (ticket != 0) st_volatile_u64(&a.scan_state[ticket], SCAN_FLAG_PREFIX | (excl + block_total));
+      s_base = excl;
+      if (ticket == a.n_tickets - 1) {
+        const unsigned long long total = excl + block_total;
+        a.status->num_pairs = total;
+        a.status->overflow = total > a.pair_capacity ? 1u : 0u;
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned long long base = s_base;
+  if (base + block_total > a.pair_capacity) return;  // overflow: the host re-runs with a larger capacity
+
+  // ---- emit (key, value) pairs -----------------------------------------------------------------
+  const unsigned long long off = base + my_excl;
+  const uint32_t dbits = __float_as_uint(depth);
+  const uint32_t vhi = (uint32_t)view << a.tile_bits;
+  const uint32_t gidx = (uint32_t)(i0 + tid);
+  const bool big = tiles > (uint32_t)WARP_EMIT_THRESHOLD;
+  if (tiles > 0 && !big) {
+    unsigned long long o = off;
+    for (int y = ry0; y < ry1; y++)
+      for (int x = rx0; x < rx1; x++) {
+        a.keys[o] = ((uint64_t)(vhi | (uint32_t)(y * a.grid_x + x)) << 32) | dbits;
+        a.vals[o] = gidx;
+        o++;
+      }
+  }
+  uint32_t bmask = __ballot_sync(0xffffffffu, big);
+  while (bmask) {
+    const int src = __ffs(bmask) - 1;
+    bmask &= bmask - 1;
+    const int x0 = __shfl_sync(0xffffffffu, rx0, src), y0 = __shfl_sync(0xffffffffu, ry0, src);
+    const int w = __shfl_sync(0xffffffffu, rx1, src) - x0;
+    const uint32_t cnt = __shfl_sync(0xffffffffu, tiles, src);
+    const unsigned long long o = __shfl_sync(0xffffffffu, off, src);
+    const uint32_t db = __shfl_sync(0xffffffffu, dbits, src), gi = __shfl_sync(0xffffffffu, gidx, src);
+    for (uint32_t k = lane; k < cnt; k += 32) {
+      const int yy = y0 + (int)(k / (uint32_t)w), xx = x0 + (int)(k % (uint32_t)w);
+      a.keys[o + k] = ((uint64_t)(vhi | (uint32_t)(yy * a.grid_x + xx)) << 32) | db;
+      a.vals[o + k] = gi;
+    }
+  }
+}
+
+}  // namespace b200s
+
+// ---- host launcher (called from api.cu) --------------------------------------------------------
+namespace b200s {
+cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, const B200sPlan& plan, char* saved, char* scratch,
+                                  const B200sOut* out, cudaStream_t stream) {
+  PreArgs a;
+  a.N = sc.num_gaussians; a.VV = vw.num_views; a.H = vw.height; a.W = vw.width;
+  a.grid_x = plan.grid_x; a.grid_y = plan.grid_y; a.tile_bits = plan.tile_bits;
+  a.chunks = (sc.num_gaussians + PRE_THREADS - 1) / PRE_THREADS;
+  a.n_tickets = plan.pre_tickets;
+  a.pair_capacity = (unsigned long long)plan.pair_capacity;
+  a.cov_floats = sc.cov_layout == B200S_COV_UPPER6 ? 6 : 9;
+  a.col_floats = sc.colors_precomp ? 3 : 3 * sc.sh_coeffs;
+  a.col_stride = a.col_floats | 1;
+  a.fpg = 3 + a.cov_floats + 1 + a.col_stride;
+  a.rec = reinterpret_cast<Rec*>(saved + plan.off_rec);
+  // the sort ping-pongs `sort_passes` times and must end in the A buffers
+  const bool start_in_a = (plan.sort_passes % 2) == 0;
+  a.keys = reinterpret_cast<uint64_t*>(scratch + (start_in_a ? plan.off_keys_a : plan.off_keys_b));
+  a.vals = start_in_a ? reinterpret_cast<uint32_t*>(saved + plan.off_vals_a) : reinterpret_cast<uint32_t*>(scratch + plan.off_vals_b);
+  a.scan_state = reinterpret_cast<uint64_t*>(scratch + plan.off_scan_state);
+  a.counters = reinterpret_cast<uint32_t*>(scratch + plan.off_counters);
+  a.status = reinterpret_cast<B200sStatus*>(saved + plan.off_status);
+  a.radii = out ? out->radii : nullptr;
+
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(a.status, 0, sizeof(B200sStatus), stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(a.counters, 0, CNT_WORDS * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(a.scan_state, 0, (size_t)plan.pre_tickets * sizeof(uint64_t), stream)) != cudaSuccess) return e;
+  size_t smem = (size_t)PRE_THREADS * a.fpg * sizeof(float);
+  if (smem < (size_t)PRE_THREADS * sizeof(Rec)) smem = (size_t)PRE_THREADS * sizeof(Rec);
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    if ((e = cudaFuncSetAttribute(preprocess_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    configured = smem;
+  }
+  if (plan.pre_tickets > 0) preprocess_bin_kernel<<<plan.pre_tickets, PRE_THREADS, smem, stream>>>(sc, vw, a);
+  return cudaGetLastError();
+}
+}  // namespace b200s

@@ -1,0 +1,302 @@
+// sort.cu -- hand-written onesweep LSD radix sort of (u64 key, u32 value) pairs + tile ranges.
+// Replaces cub::DeviceRadixSort::SortPairs and identifyTileRanges.  No CUB.
+//
+//   digit_histogram_kernel : one read of the keys, all passes' 256-bin histograms at once
+//                            (per-warp private shared-memory histograms, warp-aggregated by digit match)
+//   digit_scan_kernel      : exclusive scan of each histogram -> global digit bases
+//   onesweep_pass_kernel   : per pass, one read + one write of the pairs: stable in-tile ranking,
+//                            single-pass chained scan (decoupled look-back) of the per-tile digit
+//                            counts, reorder through shared memory, coalesced scatter
+//   tile_ranges_kernel     : (start,end) of every (view,tile) bin in the sorted list
+//
+// All kernels read the pair count from device memory (B200sStatus.num_pairs) so that no host
+// synchronisation is needed between duplication and sort; grids are sized for the capacity and
+// surplus blocks exit.  HBM-bound: 8 B/key (histogram) + 24 B/pair/pass.
+#include "kernels.cuh"
+
+namespace b200s {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per tile
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int RADIX = 256;
+constexpr uint32_t LB_FLAG_AGG = 1u << 30, LB_FLAG_PREFIX = 2u << 30, LB_VALUE_MASK = (1u << 30) - 1;
+
+__device__ __forceinline__ unsigned long long resolve_count(const CountRef& c) {
+  if (c.overflow_dev && *c.overflow_dev) return 0ull;
+  return c.n_dev ? *c.n_dev : c.n_host;
+}
+
+// lanes of the warp holding the same 8-bit digit (all 32 lanes must call)
+__device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+#if defined(B200S_MATCH_BALLOT)
+  uint32_t peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t m = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? m : ~m;
+  }
+  return peers;
+#else
+  return __match_any_sync(0xffffffffu, d);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS) digit_histogram_kernel(const uint64_t* __restrict__ keys, CountRef cnt, uint32_t* __restrict__ hist,
+                                                                       int passes) {
+  extern __shared__ uint32_t s_hist[];  // [SORT_WARPS][passes][256]
+  const unsigned long long n = resolve_count(cnt);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < SORT_WARPS * passes * RADIX; i += SORT_THREADS) s_hist[i] = 0;
+  __syncthreads();
+  uint32_t* my = s_hist + warp * passes * RADIX;
+  const unsigned long long stride = (unsigned long long)gridDim.x * SORT_THREADS;
+  // every warp iterates the same number of times so that the warp-wide match is always convergent
+  for (unsigned long long base = (unsigned long long)blockIdx.x * SORT_THREADS + warp * 32; base < n; base += stride) {
+    const unsigned long long idx = base + lane;
+    const bool valid = idx < n;
+    const uint64_t k = valid ? __ldg(keys + idx) : 0ull;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    for (int p = 0; p < passes; p++) {
+      const uint32_t d = (uint32_t)(k >> (8 * p)) & 255u;
+      const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+      if (__all_sync(0xffffffffu, d == d0)) {
+        if (lane == 0) my[p * RADIX + d0] += __popc(vmask);
+      } else {
+        const uint32_t peers = match_digit(d) & vmask;
+        if (valid && lane == (__ffs(peers) - 1)) my[p * RADIX + d] += __popc(peers);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int p = 0; p < passes; p++) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) s += s_hist[(w * passes + p) * RADIX + tid];
+    if (s) atomicAdd(&hist[p * RADIX + tid], s);
+  }
+}
+
+// one block; exclusive scan of each pass's histogram in place
+__global__ void __launch_bounds__(RADIX) digit_scan_kernel(uint32_t* hist, int passes) {
+  __shared__ uint32_t s_w[RADIX / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int p = 0; p < passes; p++) {
+    const uint32_t v = hist[p * RADIX + tid];
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < warp; w++) off += s_w[w];
+    hist[p * RADIX + tid] = off + incl - v;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PassArgs {
+  const uint64_t* keys_in; const uint32_t* vals_in;
+  uint64_t* keys_out; uint32_t* vals_out;
+  const uint32_t* gbase;   // [256] exclusive digit bases of this pass
+  uint32_t* lb_cur;        // [tiles][256] look-back words of this pass (zeroed)
+  uint32_t* lb_next;       // same for the next pass: this pass zeroes the rows it owns
+  uint32_t* tile_counter;  // dynamic tile id
+  CountRef cnt;
+  int shift;
+};
+
+__global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const PassArgs a) {
+  __shared__ __align__(16) uint64_t s_keys[SORT_TILE];  // reused as u32 values
+  __shared__ uint32_t s_wc[SORT_WARPS][RADIX];
+  __shared__ uint32_t s_goff[RADIX];
+  __shared__ uint32_t s_dstart[RADIX];
+  __shared__ uint32_t s_scan[SORT_WARPS];
+  __shared__ uint32_t s_tile;
+
+  const unsigned long long n = resolve_count(a.cnt);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
+#pragma unroll
+  for (int w = 0; w < SORT_WARPS; w++) s_wc[w][tid] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const unsigned long long base = (unsigned long long)tile * SORT_TILE;
+  if (base >= n) return;
+  const uint32_t nvalid = (uint32_t)min((unsigned long long)SORT_TILE, n - base);
+  a.lb_next[(size_t)tile * RADIX + tid] = 0;
+
+  // ---- load keys, warp-striped: item i of lane l of warp w is element w*512 + i*32 + l of the tile
+  uint64_t key[SORT_ITEMS];
+  const uint32_t wbase = warp * (32 * SORT_ITEMS) + lane;
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const uint32_t e = wbase + i * 32;
+    key[i] = e < nvalid ? __ldg(a.keys_in + base + e) : ~0ull;
+  }
+  // ---- stable rank inside the warp, item by item
+  uint32_t rank[SORT_ITEMS];
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t* wc = s_wc[warp];
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const uint32_t d = (uint32_t)(key[i] >> a.shift) & 255u;
+    const uint32_t peers = match_digit(d);
+    const uint32_t r = wc[d];
+    __syncwarp();
+    if (lane == (__ffs(peers) - 1)) wc[d] = r + __popc(peers);
+    __syncwarp();
+    rank[i] = r + __popc(peers & lt);
+  }
+  __syncthreads();
+  // ---- thread = digit: exclusive scan over warps, tile count, chained scan across tiles
+  uint32_t run = 0;
+#pragma unroll
+  for (int w = 0; w < SORT_WARPS; w++) { const uint32_t t = s_wc[w][tid]; s_wc[w][tid] = run; run += t; }
+  uint32_t prev = 0;
+  {
+    uint32_t* row = a.lb_cur + (size_t)tile * RADIX + tid;
+    if (tile == 0) {
+      st_volatile_u32(row, LB_FLAG_PREFIX | run);
+    } else {
+      st_volatile_u32(row, LB_FLAG_AGG | run);
+      int t = (int)tile - 1;
+      while (true) {
+        const uint32_t w = ld_volatile_u32(a.lb_cur + (size_t)t * RADIX + tid);
+        const uint32_t f = w >> 30;
+        if (f == 0) continue;
+        prev += w & LB_VALUE_MASK;
+        if (f == 2) break;
+        t--;
+      }
+      st_volatile_u32(row, LB_FLAG_PREFIX | (prev + run));
+    }
+  }
+  // ---- exclusive scan over digits of the tile counts -> start of each digit inside the tile
+  uint32_t incl = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+#pragma unroll
+  for (int w = 0; w < SORT_WARPS; w++) if (w < warp) woff += s_scan[w];
+  const uint32_t dstart = woff + incl - run;
+  s_dstart[tid] = dstart;
+  s_goff[tid] = a.gbase[tid] + prev - dstart;
+  __syncthreads();
+  // ---- reorder keys through shared memory
+  uint32_t pos[SORT_ITEMS];
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const uint32_t d = (uint32_t)(key[i] >> a.shift) & 255u;
+    pos[i] = s_dstart[d] + wc[d] + rank[i];
+    s_keys[pos[i]] = key[i];
+  }
+  __syncthreads();
+  uint32_t gpos[SORT_ITEMS];
+#pragma unroll
+  for (int j = 0; j < SORT_ITEMS; j++) {
+    const uint32_t e = j * SORT_THREADS + tid;
+    const uint64_t k = s_keys[e];
+    gpos[j] = s_goff[(uint32_t)(k >> a.shift) & 255u] + e;
+    if (e < nvalid) a.keys_out[gpos[j]] = k;
+  }
+  __syncthreads();
+  // ---- values take the same route
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys);
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    const uint32_t e = wbase + i * 32;
+    if (e < nvalid) s_vals[pos[i]] = __ldg(a.vals_in + base + e);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < SORT_ITEMS; j++) {
+    const uint32_t e = j * SORT_THREADS + tid;
+    if (e < nvalid) a.vals_out[gpos[j]] = s_vals[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __restrict__ keys, CountRef cnt, uint2* __restrict__ ranges) {
+  const unsigned long long n = resolve_count(cnt);
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+    const uint32_t cur = (uint32_t)(__ldg(keys + idx) >> 32);
+    if (idx == 0) ranges[cur].x = 0;
+    else {
+      const uint32_t prv = (uint32_t)(__ldg(keys + idx - 1) >> 32);
+      if (cur != prv) { ranges[prv].y = (uint32_t)idx; ranges[cur].x = (uint32_t)idx; }
+    }
+    if (idx == n - 1) ranges[cur].y = (uint32_t)n;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+size_t sort_tmp_bytes(long long n_cap) {
+  const size_t tiles = (size_t)((n_cap + SORT_TILE - 1) / SORT_TILE) + 1;
+  return 8 * RADIX * sizeof(uint32_t) + 2 * tiles * RADIX * sizeof(uint32_t) + CNT_WORDS * sizeof(uint32_t);
+}
+int sort_tiles_for(long long n_cap) { return (int)((n_cap + SORT_TILE - 1) / SORT_TILE) + 1; }
+
+// Sorts on the low `passes*8` bits.  Input in (keys_in, vals_in) = A if passes is even, else B;
+// the output always ends in the A buffers.  hist [8*256], lookback [2*tiles*256], counters [CNT_WORDS].
+cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int passes, long long n_cap,
+                        CountRef cnt, uint32_t* hist, uint32_t* lookback, uint32_t* counters, int sm_count, cudaStream_t stream) {
+  if (passes <= 0 || n_cap <= 0) return cudaSuccess;
+  cudaError_t e;
+  const int tiles = sort_tiles_for(n_cap);
+  if ((e = cudaMemsetAsync(hist, 0, 8 * RADIX * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(counters + CNT_SORT_TILE0, 0, 8 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+  const bool start_in_a = (passes % 2) == 0;
+  uint64_t* kin = start_in_a ? keys_a : keys_b; uint32_t* vin = start_in_a ? vals_a : vals_b;
+  uint64_t* kout = start_in_a ? keys_b : keys_a; uint32_t* vout = start_in_a ? vals_b : vals_a;
+  {
+    const size_t smem = (size_t)SORT_WARPS * passes * RADIX * sizeof(uint32_t);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+      if ((e = cudaFuncSetAttribute(digit_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      configured = smem;
+    }
+    long long blocks = (n_cap + SORT_THREADS * 16 - 1) / (SORT_THREADS * 16);
+    const long long max_blocks = (long long)sm_count * 4;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    digit_histogram_kernel<<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+    digit_scan_kernel<<<1, RADIX, 0, stream>>>(hist, passes);
+  }
+  for (int p = 0; p < passes; p++) {
+    PassArgs a;
+    a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout;
+    a.gbase = hist + p * RADIX;
+    a.lb_cur = lookback + (size_t)(p & 1) * tiles * RADIX;
+    a.lb_next = lookback + (size_t)((p + 1) & 1) * tiles * RADIX;
+    a.tile_counter = counters + CNT_SORT_TILE0 + p;
+    a.cnt = cnt; a.shift = 8 * p;
+    onesweep_pass_kernel<<<tiles - 1 > 0 ? tiles - 1 : 1, SORT_THREADS, 0, stream>>>(a);
+    uint64_t* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = vin; vin = vout; vout = tv;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tile_ranges(const uint64_t* keys, CountRef cnt, uint2* ranges, int bins, long long n_cap, int sm_count, cudaStream_t stream) {
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(ranges, 0, (size_t)bins * sizeof(uint2), stream)) != cudaSuccess) return e;
+  long long blocks = (n_cap + 256 * 8 - 1) / (256 * 8);
+  const long long max_blocks = (long long)sm_count * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  tile_ranges_kernel<<<(int)blocks, 256, 0, stream>>>(keys, cnt, ranges);
+  return cudaGetLastError();
+}
+
+}  // namespace b200s

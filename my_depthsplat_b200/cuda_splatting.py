@@ -1,0 +1,237 @@
+"""Drop-in for src/model/decoder/cuda_splatting.py of the reference.
+
+Same public names, argument meaning and results:
+    get_projection_matrix      (reference :16-43)
+    render_cuda                (reference :46-126)
+    render_cuda_orthographic   (reference :129-219)
+    render_depth_cuda          (reference :225-264)
+    DepthRenderingMode         (reference :222)
+
+What differs is below the signatures: no per-view Python loop, no ``.item()`` syncs, no SH / covariance
+re-layout copies, no second rasterization for depth -- one call into the sm_100a library for all
+views (my_depthsplat_b200.rasterizer).  The scale-invariant normalisation of the Gaussians
+(reference :63-70) is folded into the projection kernel; the camera matrices are built with the same
+torch operations as the reference so that they are bit-identical.
+
+``render_views`` is the multi-view entry the decoder uses: Gaussians stay ``[B,N,...]``, cameras are
+``[B,V,...]``; nothing is replicated per view.
+"""
+from __future__ import annotations
+
+from math import isqrt
+from typing import Literal, Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .projection import get_fov, homogenize_points
+from .rasterizer import ViewPack, rasterize
+
+DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
+
+
+def get_projection_matrix(near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tensor) -> Tensor:
+    """[b] each -> [b,4,4].  Maps the viewing frustum to (-1, 1) in X/Y and (0, 1) in Z, with w = z
+    (Z is not flipped to (-1, 1) as OpenGL would)."""
+    tan_x = (0.5 * fov_x).tan()
+    tan_y = (0.5 * fov_y).tan()
+    top, right = tan_y * near, tan_x * near
+    bottom, left = -top, -right
+    proj = torch.zeros((near.shape[0], 4, 4), dtype=torch.float32, device=near.device)
+    proj[:, 0, 0] = 2 * near / (right - left)
+    proj[:, 1, 1] = 2 * near / (top - bottom)
+    proj[:, 0, 2] = (right + left) / (right - left)
+    proj[:, 1, 2] = (top + bottom) / (top - bottom)
+    proj[:, 3, 2] = 1
+    proj[:, 2, 2] = far / (far - near)
+    proj[:, 2, 3] = -(far * near) / (far - near)
+    return proj
+
+
+def _camera_block(extrinsics: Tensor, near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tensor, tan_fov_x: Tensor,
+                  tan_fov_y: Tensor):
+    """View / full-projection matrices in the transposed storage the rasterizer consumes, camera
+    positions and tanfov -- the reference's lines :83-86 and :101-110, batched."""
+    projection = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
+    view = extrinsics.inverse().transpose(1, 2)
+    full = view @ projection
+    campos = extrinsics[:, :3, 3]
+    tanfov = torch.stack([tan_fov_x.expand(near.shape[0]), tan_fov_y.expand(near.shape[0])], dim=-1)
+    return view.contiguous(), full.contiguous(), campos.contiguous(), tanfov.to(torch.float32).contiguous()
+
+
+def _depth_block(extrinsics_raw: Tensor, near_raw: Tensor, far_raw: Tensor):
+    """Row 2 of the UNnormalised world->camera matrix: z_cam = row . (mean, 1) (reference :238-241)."""
+    w2c = extrinsics_raw.inverse()
+    return w2c[:, 2, :].contiguous(), torch.stack([near_raw, far_raw], dim=-1).contiguous()
+
+
+def render_views(
+    extrinsics: Tensor,            # [B,V,4,4] camera-to-world, OpenCV
+    intrinsics: Tensor,            # [B,V,3,3] normalised
+    near: Tensor,                  # [B,V]
+    far: Tensor,                   # [B,V]
+    image_shape: tuple[int, int],
+    background_color: Tensor,      # [3] or [B,V,3]
+    gaussian_means: Tensor,        # [B,N,3]
+    gaussian_covariances: Tensor,  # [B,N,3,3]
+    gaussian_sh_coefficients: Tensor,  # [B,N,3,d_sh]
+    gaussian_opacities: Tensor,    # [B,N]
+    scale_invariant: bool = True,
+    use_sh: bool = True,
+    depth_mode: Optional[DepthRenderingMode] = None,
+    want_radii: bool = False,
+    count_work: bool = False,
+):
+    """All V views of all B scenes in one rasterizer call.  Returns (color [B,V,3,H,W],
+    depth [B,V,H,W] | None) (+ radii [B,V,N] when want_radii)."""
+    B, V = extrinsics.shape[:2]
+    h, w = image_shape
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    dev = gaussian_means.device
+    ext = extrinsics.reshape(B * V, 4, 4).to(torch.float32)
+    K = intrinsics.reshape(B * V, 3, 3).to(torch.float32)
+    near_f, far_f = near.reshape(B * V).to(torch.float32), far.reshape(B * V).to(torch.float32)
+
+    depth_affine = depth_clamp = None
+    if depth_mode is not None:
+        depth_affine, depth_clamp = _depth_block(ext, near_f, far_f)
+
+    scale_pack = None
+    if scale_invariant:
+        scale = 1 / near_f
+        ext = ext.clone()
+        ext[..., :3, 3] = ext[..., :3, 3] * scale[:, None]
+        scale_pack = torch.stack([scale, scale ** 2], dim=-1).contiguous()
+        near_f = near_f * scale
+        far_f = far_f * scale
+
+    fov_x, fov_y = get_fov(K).unbind(dim=-1)
+    tan_fov_x, tan_fov_y = (0.5 * fov_x).tan(), (0.5 * fov_y).tan()
+    view, full, campos, tanfov = _camera_block(ext, near_f, far_f, fov_x, fov_y, tan_fov_x, tan_fov_y)
+
+    bg = background_color.to(device=dev, dtype=torch.float32)
+    bg = bg.expand(B, V, 3).reshape(B * V, 3).contiguous() if bg.dim() == 1 else bg.reshape(B * V, 3).contiguous()
+    scene_index = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(V)
+
+    pack = ViewPack(scene_index, view, full, campos, tanfov, bg, h, w, scale_pack, depth_mode, depth_affine, depth_clamp)
+    if use_sh:
+        degree = isqrt(gaussian_sh_coefficients.shape[-1]) - 1
+        colors = gaussian_sh_coefficients
+    else:
+        degree = 0
+        colors = gaussian_sh_coefficients[..., 0]
+    color, depth, radii = rasterize(gaussian_means, gaussian_covariances, colors, gaussian_opacities, pack, use_sh=use_sh,
+                                    sh_degree=degree, sh_layout=_lib.SH_CHANNEL_MAJOR, want_radii=want_radii, count_work=count_work)
+    color = color.reshape(B, V, 3, h, w)
+    depth = None if depth is None else depth.reshape(B, V, h, w)
+    if want_radii:
+        return color, depth, radii.reshape(B, V, -1)
+    return color, depth
+
+
+def render_cuda(
+    extrinsics: Tensor,                # [batch,4,4]
+    intrinsics: Tensor,                # [batch,3,3]
+    near: Tensor,                      # [batch]
+    far: Tensor,                       # [batch]
+    image_shape: tuple[int, int],
+    background_color: Tensor,          # [batch,3]
+    gaussian_means: Tensor,            # [batch,gaussian,3]
+    gaussian_covariances: Tensor,      # [batch,gaussian,3,3]
+    gaussian_sh_coefficients: Tensor,  # [batch,gaussian,3,d_sh]
+    gaussian_opacities: Tensor,        # [batch,gaussian]
+    scale_invariant: bool = True,
+    use_sh: bool = True,
+) -> Tensor:
+    """-> [batch,3,height,width].  Every batch element is its own (scene, camera) pair, as in the
+    reference; all of them are rendered by one call."""
+    color, _ = render_views(
+        extrinsics[:, None], intrinsics[:, None], near[:, None], far[:, None], image_shape, background_color[:, None],
+        gaussian_means, gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities,
+        scale_invariant=scale_invariant, use_sh=use_sh,
+    )
+    return color[:, 0]
+
+
+def render_cuda_orthographic(
+    extrinsics: Tensor,                # [batch,4,4]
+    width: Tensor,                     # [batch]
+    height: Tensor,                    # [batch]
+    near: Tensor,                      # [batch]
+    far: Tensor,                       # [batch]
+    image_shape: tuple[int, int],
+    background_color: Tensor,          # [batch,3]
+    gaussian_means: Tensor,            # [batch,gaussian,3]
+    gaussian_covariances: Tensor,      # [batch,gaussian,3,3]
+    gaussian_sh_coefficients: Tensor,  # [batch,gaussian,3,d_sh]
+    gaussian_opacities: Tensor,        # [batch,gaussian]
+    fov_degrees: float = 0.1,
+    use_sh: bool = True,
+    dump: dict | None = None,
+) -> Tensor:
+    """-> [batch,3,height,width].  "Orthographic" = a camera moved far back with a tiny field of view
+    (reference :129-219); same kernels, different matrices, no scale-invariant normalisation."""
+    b = extrinsics.shape[0]
+    h, w = image_shape
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    dev = extrinsics.device
+
+    fov_x = torch.tensor(fov_degrees, device=dev).deg2rad()
+    tan_fov_x = (0.5 * fov_x).tan()
+    distance_to_near = (0.5 * width) / tan_fov_x
+    tan_fov_y = 0.5 * height / distance_to_near
+    fov_y = (2 * tan_fov_y).atan()
+    near = near + distance_to_near
+    far = far + distance_to_near
+    move_back = torch.eye(4, dtype=torch.float32, device=dev)
+    move_back[2, 3] = -distance_to_near
+    extrinsics = extrinsics @ move_back
+
+    if dump is not None:  # escape hatch for visualisation code, as in the reference
+        dump["extrinsics"] = extrinsics
+        dump["fov_x"] = fov_x
+        dump["fov_y"] = fov_y
+        dump["near"] = near
+        dump["far"] = far
+
+    view, full, campos, tanfov = _camera_block(extrinsics.to(torch.float32), near, far, fov_x.expand(b), fov_y, tan_fov_x, tan_fov_y)
+    scene_index = torch.arange(b, device=dev, dtype=torch.int32)
+    bg = background_color.to(device=dev, dtype=torch.float32).reshape(b, 3).contiguous()
+    pack = ViewPack(scene_index, view, full, campos, tanfov, bg, h, w)
+    if use_sh:
+        degree, colors = isqrt(gaussian_sh_coefficients.shape[-1]) - 1, gaussian_sh_coefficients
+    else:
+        degree, colors = 0, gaussian_sh_coefficients[..., 0]
+    color, _, _ = rasterize(gaussian_means, gaussian_covariances, colors, gaussian_opacities, pack, use_sh=use_sh, sh_degree=degree)
+    return color
+
+
+def render_depth_cuda(
+    extrinsics: Tensor,            # [batch,4,4]
+    intrinsics: Tensor,            # [batch,3,3]
+    near: Tensor,                  # [batch]
+    far: Tensor,                   # [batch]
+    image_shape: tuple[int, int],
+    gaussian_means: Tensor,        # [batch,gaussian,3]
+    gaussian_covariances: Tensor,  # [batch,gaussian,3,3]
+    gaussian_opacities: Tensor,    # [batch,gaussian]
+    scale_invariant: bool = True,
+    mode: DepthRenderingMode = "depth",
+) -> Tensor:
+    """-> [batch,height,width]: alpha-composited camera-space depth (or 1/z, or the reference's
+    clamped log) over a zero background."""
+    b, g = gaussian_opacities.shape
+    dummy = torch.zeros((b, g, 3, 1), dtype=torch.float32, device=gaussian_means.device)
+    _, depth = render_views(
+        extrinsics[:, None], intrinsics[:, None], near[:, None], far[:, None], image_shape,
+        torch.zeros((b, 1, 3), dtype=torch.float32, device=gaussian_means.device),
+        gaussian_means, gaussian_covariances, dummy, gaussian_opacities,
+        scale_invariant=scale_invariant, use_sh=False, depth_mode=mode,
+    )
+    return depth[:, 0]
+
+
+__all__ = ["DepthRenderingMode", "get_projection_matrix", "render_cuda", "render_cuda_orthographic", "render_depth_cuda",
+           "render_views", "homogenize_points"]

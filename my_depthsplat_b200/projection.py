@@ -1,0 +1,35 @@
+"""The two camera helpers the hot path uses from src/geometry/projection.py of the reference
+(get_fov :233-247, homogenize_points :9-13).  The sequence of torch operations is kept (inverse,
+mat-vec, normalise, dot, acos) so that the field of view -- and hence tanfov, focal lengths and
+tile rects -- comes out bit-identical to the reference's for the same normalised intrinsics.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+# mid-points of the left, right, top and bottom image edges in normalised image coordinates
+_EDGE_MIDPOINTS = ((0.0, 0.5), (1.0, 0.5), (0.5, 0.0), (0.5, 1.0))
+
+
+def homogenize_points(points: Tensor) -> Tensor:
+    """(..., d) -> (..., d+1) with a trailing one."""
+    one = torch.ones_like(points[..., :1])
+    return torch.cat([points, one], dim=-1)
+
+
+def _unit_ray(k_inv: Tensor, u: float, v: float) -> Tensor:
+    pixel = torch.tensor([u, v, 1.0], dtype=torch.float32, device=k_inv.device)
+    ray = torch.einsum("bij,j->bi", k_inv, pixel)
+    return ray / ray.norm(dim=-1, keepdim=True)
+
+
+def get_fov(intrinsics: Tensor) -> Tensor:
+    """Normalised intrinsics [b,3,3] -> [b,2] = (fov_x, fov_y): the angle between the unprojected
+    rays through opposite edge mid-points.  The principal point does not survive this (the
+    frustum built from it is symmetric), exactly as in the reference."""
+    k_inv = intrinsics.inverse()
+    left, right, top, bottom = (_unit_ray(k_inv, u, v) for u, v in _EDGE_MIDPOINTS)
+    fov_x = (left * right).sum(dim=-1).acos()
+    fov_y = (top * bottom).sum(dim=-1).acos()
+    return torch.stack((fov_x, fov_y), dim=-1)

@@ -1,0 +1,245 @@
+"""Multi-view differentiable rasterization: torch.autograd.Function over the C-ABI library.
+
+One call renders ALL (scene, camera) views of a batch from the un-replicated ``[B,N,...]`` Gaussian
+tensors.  It replaces, in one go, what the reference does per view in a Python loop
+(src/model/decoder/cuda_splatting.py:90-125): GaussianRasterizer(settings)(means3D, means2D, shs |
+colors_precomp, opacities, cov3D_precomp), including the autograd of the per-view replication
+(decoder_splatting_cuda.py:53-56) and the second, depth-as-colour render
+(cuda_splatting.py:250-263).
+
+PyTorch here is plumbing only: device memory (caching allocator), the current stream, autograd.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_DEPTH_MODES = {None: _lib.DEPTH_NONE, "depth": _lib.DEPTH_Z, "relative_disparity": _lib.DEPTH_Z,
+                "disparity": _lib.DEPTH_DISPARITY, "log": _lib.DEPTH_LOG}
+
+
+@dataclass
+class ViewPack:
+    """Per-view camera block (all fp32 CUDA tensors, VV = number of views of the call)."""
+    scene_index: torch.Tensor          # [VV] int32
+    viewmatrix: torch.Tensor           # [VV,4,4] transposed storage (cuda_splatting.py:85)
+    projmatrix: torch.Tensor           # [VV,4,4] transposed storage (cuda_splatting.py:86)
+    campos: torch.Tensor               # [VV,3]
+    tanfov: torch.Tensor               # [VV,2]
+    background: torch.Tensor           # [VV,3]
+    height: int
+    width: int
+    scale: Optional[torch.Tensor] = None         # [VV,2] (s, s^2) or None
+    depth_mode: Optional[str] = None
+    depth_affine: Optional[torch.Tensor] = None  # [VV,4]
+    depth_clamp: Optional[torch.Tensor] = None   # [VV,2]
+
+
+@dataclass
+class RenderStats:
+    num_pairs: int = 0
+    num_visible: int = 0
+    tested: int = 0
+    blended: int = 0
+    max_tile_len: int = 0
+    pair_capacity: int = 0
+    retries: int = 0
+
+
+_capacity_hint: dict = {}
+_scratch_cache: dict = {}
+last_stats = RenderStats()
+# parity tests set debug_keep to look at the stage outputs (records, sorted keys, ranges) of the last call
+debug_keep = False
+debug_last: Optional[dict] = None
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the rasterizer has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _scratch(device, nbytes: int) -> torch.Tensor:
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _scratch_cache.pop(key, None)
+        buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)
+        _scratch_cache[key] = buf
+    return buf
+
+
+def release_scratch() -> None:
+    _scratch_cache.clear()
+
+
+class _Ctx:
+    pass
+
+
+def _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp: ViewPack):
+    B, N = means.shape[0], means.shape[1]
+    sc = _lib.Scene()
+    sc.num_scenes, sc.num_gaussians = B, N
+    sc.cov_layout = _lib.COV_UPPER6 if covs.shape[-1] == 6 and covs.dim() == 3 else _lib.COV_3X3
+    sc.means, sc.covariances, sc.opacities = _ptr(means), _ptr(covs), _ptr(opacities)
+    if use_sh:
+        d_sh = colors.shape[-1] if sh_layout == _lib.SH_CHANNEL_MAJOR else colors.shape[-2]
+        sc.sh_degree, sc.sh_coeffs, sc.sh_layout = sh_degree, d_sh, sh_layout
+        sc.harmonics, sc.colors_precomp = _ptr(colors), None
+    else:
+        sc.sh_degree, sc.sh_coeffs, sc.sh_layout = 0, 1, _lib.SH_CHANNEL_MAJOR
+        sc.harmonics, sc.colors_precomp = None, _ptr(colors)
+    vw = _lib.Views()
+    vw.num_views, vw.height, vw.width = vp.scene_index.shape[0], vp.height, vp.width
+    vw.depth_mode = _DEPTH_MODES[vp.depth_mode]
+    vw.scene_index, vw.viewmatrix, vw.projmatrix = _ptr(vp.scene_index), _ptr(vp.viewmatrix), _ptr(vp.projmatrix)
+    vw.campos, vw.tanfov, vw.background = _ptr(vp.campos), _ptr(vp.tanfov), _ptr(vp.background)
+    vw.scale, vw.depth_affine, vw.depth_clamp = _ptr(vp.scale), _ptr(vp.depth_affine), _ptr(vp.depth_clamp)
+    return sc, vw
+
+
+class _Rasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, covs, colors, opacities, means2d, vp: ViewPack, use_sh: bool, sh_degree: int, sh_layout: int,
+                want_radii: bool, count_work: bool):
+        L = _lib.load()
+        dev = means.device
+        B, N = means.shape[0], means.shape[1]
+        VV, H, W = vp.scene_index.shape[0], vp.height, vp.width
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        sc, vw = _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp)
+
+        color = torch.empty((VV, 3, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((VV, H, W), dtype=torch.float32, device=dev) if vp.depth_mode is not None else None
+        radii = torch.empty((VV, N), dtype=torch.int32, device=dev) if want_radii else None
+        out = _lib.Out(_ptr(color), _ptr(depth), _ptr(radii), 1 if count_work else 0)
+
+        key = (dev.index, B, N, VV, H, W)
+        cap = _capacity_hint.get(key) or max(4 * N * VV, 1 << 16)
+        cap = min(cap, (1 << 30) - 1)
+        host = torch.empty(8, dtype=torch.int64, pin_memory=True)
+        retries = 0
+        while True:
+            plan = _lib.plan(B, N, VV, H, W, cap)
+            saved = torch.empty(plan.saved_bytes, dtype=torch.uint8, device=dev)
+            scratch = _scratch(dev, plan.scratch_bytes)
+            _lib.check(L.b200s_forward_bin(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(),
+                                           C.byref(out), stream), "b200s_forward_bin")
+            # the pair count travels to the host while the GPU already sorts and composites
+            host.copy_(saved[:64].view(torch.int64), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            _lib.check(L.b200s_forward_render(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(),
+                                              C.byref(out), stream), "b200s_forward_render")
+            ev.synchronize()
+            num_pairs = int(host[0].item())
+            overflow = int(host[1].item()) & 0xFFFFFFFF
+            if not overflow:
+                break
+            if num_pairs >= (1 << 30) - 1:
+                raise RuntimeError(f"{num_pairs} (tile, Gaussian) pairs in one call exceed the 2^30 limit; render fewer views per call")
+            cap = min(int(num_pairs * 1.25) + 4096, (1 << 30) - 1)
+            retries += 1
+        _capacity_hint[key] = min(max(int(num_pairs * 1.25) + 4096, 1 << 16), (1 << 30) - 1)
+
+        st = last_stats
+        st.num_pairs, st.num_visible = num_pairs, (int(host[1].item()) >> 32) & 0xFFFFFFFF
+        st.pair_capacity, st.retries = cap, retries
+        if count_work:
+            torch.cuda.current_stream(dev).synchronize()
+            h = saved[:64].view(torch.int64).cpu()
+            st.tested, st.blended, st.max_tile_len = int(h[2]), int(h[3]), int(h[4]) & 0xFFFFFFFF
+
+        if debug_keep:
+            global debug_last
+            debug_last = dict(plan=plan, saved=saved, scratch=scratch, num_pairs=num_pairs, N=N, VV=VV, H=H, W=W)
+        ctx.save_for_backward(means, covs, colors, opacities)
+        ctx.b200 = (vp, use_sh, sh_degree, sh_layout, plan, saved, means2d is not None)
+        outs = [color]
+        if depth is not None:
+            outs.append(depth)
+        else:
+            outs.append(color.new_empty(0))
+            ctx.mark_non_differentiable(outs[-1])
+        if radii is None:
+            radii = torch.empty(0, dtype=torch.int32, device=dev)
+        ctx.mark_non_differentiable(radii)
+        return outs[0], outs[1], radii
+
+    @staticmethod
+    def backward(ctx, g_color, g_depth, _g_radii):
+        L = _lib.load()
+        means, covs, colors, opacities = ctx.saved_tensors
+        vp, use_sh, sh_degree, sh_layout, plan, saved, want_m2d = ctx.b200
+        dev = means.device
+        VV, N = vp.scene_index.shape[0], means.shape[1]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        sc, vw = _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp)
+        g_color = (torch.zeros((VV, 3, vp.height, vp.width), dtype=torch.float32, device=dev) if g_color is None
+                   else g_color.to(torch.float32).contiguous())
+        if vp.depth_mode is not None:
+            g_depth = (torch.zeros((VV, vp.height, vp.width), dtype=torch.float32, device=dev) if g_depth is None
+                       else g_depth.to(torch.float32).contiguous())
+        else:
+            g_depth = None
+        d_means = torch.empty_like(means)
+        d_covs = torch.empty_like(covs)
+        d_colors = torch.empty_like(colors)
+        d_op = torch.empty_like(opacities)
+        d_m2d = torch.empty((VV, N, 3), dtype=torch.float32, device=dev) if want_m2d else None
+        scratch = _scratch(dev, plan.scratch_bytes)
+        gout = _lib.GradOut(_ptr(g_color), _ptr(g_depth))
+        gin = _lib.GradIn(_ptr(d_means), _ptr(d_covs), _ptr(d_colors) if use_sh else None, None if use_sh else _ptr(d_colors),
+                          _ptr(d_op), _ptr(d_m2d))
+        out = _lib.Out(None, None, None, 0)
+        _lib.check(L.b200s_backward(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(), C.byref(out),
+                                    C.byref(gout), C.byref(gin), stream), "b200s_backward")
+        return d_means, d_covs, d_colors, d_op, d_m2d, None, None, None, None, None, None
+
+
+def rasterize(means: torch.Tensor, covariances: torch.Tensor, colors: torch.Tensor, opacities: torch.Tensor, views: ViewPack, *,
+              use_sh: bool = True, sh_degree: Optional[int] = None, sh_layout: int = _lib.SH_CHANNEL_MAJOR,
+              means2d: Optional[torch.Tensor] = None, want_radii: bool = False, count_work: bool = False):
+    """means [B,N,3]; covariances [B,N,3,3] or [B,N,6]; colors = harmonics [B,N,3,d_sh] (channel-major,
+    DepthSplat layout) / [B,N,d_sh,3] (coefficient-major, extension layout) when use_sh else [B,N,3];
+    opacities [B,N].  Returns (color [VV,3,H,W], depth [VV,H,W] | None, radii [VV,N] | None)."""
+    means = _f32c(means, "means"); covariances = _f32c(covariances, "covariances")
+    colors = _f32c(colors, "colors"); opacities = _f32c(opacities, "opacities")
+    if means.dim() != 3 or means.shape[-1] != 3:
+        raise ValueError("means must be [B,N,3]")
+    B, N = means.shape[:2]
+    if covariances.shape not in ((B, N, 3, 3), (B, N, 6)):
+        raise ValueError("covariances must be [B,N,3,3] or [B,N,6]")
+    if opacities.shape != (B, N):
+        raise ValueError("opacities must be [B,N]")
+    if use_sh:
+        if colors.dim() != 4 or colors.shape[:2] != (B, N):
+            raise ValueError("harmonics must be [B,N,3,d_sh] or [B,N,d_sh,3]")
+        d_sh = colors.shape[-1] if sh_layout == _lib.SH_CHANNEL_MAJOR else colors.shape[-2]
+        if colors.shape[-2 if sh_layout == _lib.SH_CHANNEL_MAJOR else -1] != 3:
+            raise ValueError("harmonics layout does not match sh_layout")
+        if sh_degree is None:
+            sh_degree = int(round(d_sh ** 0.5)) - 1
+    else:
+        if colors.shape != (B, N, 3):
+            raise ValueError("colors_precomp must be [B,N,3]")
+        sh_degree = 0
+    if N == 0 or views.scene_index.shape[0] == 0:
+        raise ValueError("empty scene or view list")
+    color, depth, radii = _Rasterize.apply(means, covariances, colors, opacities, means2d, views, use_sh, sh_degree, sh_layout,
+                                           want_radii, count_work)
+    return color, (depth if views.depth_mode is not None else None), (radii if want_radii else None)
