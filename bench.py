@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- rendered Mpix/s forward+backward of the rasterizer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2T] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...       (one rank per GPU, NCCL)
+
+A "step" = one forward + backward of the decoder path over one batch of synthetic input:
+DecoderSplattingCUDA.forward on V target views of one scene, then the gradients of the rendered
+colour w.r.t. every Gaussian tensor.  Default workload "C2T": 6 context views at 512x960 -> 2 949 120
+pixel-aligned Gaussians (trained-like scales, scale_max 0.1), 4 target views per GPU, colour only
+(train.depth_mode is null in the reference's default config, config/main.yaml:55).
+At N > 1 the target views of the SAME scene are sharded over the ranks (Gaussians replicated, weak
+scaling: 4 views per GPU) and the per-Gaussian gradients are summed with one NCCL all-reduce inside
+the timed step.
+
+One JSON line on rank 0: value = whole-job Mpix/s with inputs resident in HBM; e2e = the same metric
+through the public decoder call with HOST (pinned) inputs and outputs, copies inside the timed region;
+roofline = the dominant kernel against its bound; cpu_baseline = the CPU oracle (a port: the reference
+has no CPU rasterizer) timed on this box's host cores on one view of the same workload.
+--impl reference times that CPU implementation as the reference arm (the third-party CUDA extension
+the reference binds is not installable here: no network, sources absent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d.get("hbm_gbs", 6650.0)), float(d.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 7]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if "Active" in v and "Not" not in v:
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+def oracle_step_inputs(scene, view: int):
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import per_view_extension_inputs
+    return per_view_extension_inputs(scene, 0, view)
+
+
+def time_oracle(scene, steps: int, warmup: int, threads: int):
+    """CPU arm: the oracle's forward + backward of ONE target view (all Gaussians, full resolution),
+    OpenMP over tiles / Gaussians on `threads` host threads.  Returns (Mpix/s, seconds per step)."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from oracle import splat_oracle as so
+    so.set_parallel_backward(True)
+    inp = oracle_step_inputs(scene, 0)
+    g = scene.grad_color[0, 0].numpy()
+    H, W = scene.image_shape
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        st = so.forward_view(**inp)
+        so.backward_view(st, g)
+        st.close()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    so.set_parallel_backward(False)
+    sec = sum(ts) / len(ts)
+    return H * W / sec / 1e6, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from my_depthsplat_b200.scenes import CONFIGS, make_scene
+    cfg = CONFIGS[args.config]
+    scene = make_scene(cfg, v_tgt=1)
+    threads = os.cpu_count() or 1
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    mpix, sec = time_oracle(scene, steps, warmup, threads)
+    H, W = scene.image_shape
+    sample = f"1 target view {H}x{W}, all {scene.gaussians.means.shape[1]} Gaussians, fwd+bwd, {steps} steps"
+    line = {
+        "impl": "reference", "metric": "rasterizer fwd+bwd Mpix/s", "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": _workload_name(cfg, scene, 4), "note": "reference arm = CPU oracle port (the reference's CUDA extension "
+                   "diff_gaussian_rasterization is not installable here and the reference has no CPU rasterizer)"},
+        "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _workload_name(cfg, scene, v):
+    H, W = scene.image_shape
+    return (f"{cfg.name}: {cfg.v_ctx} ctx views {H}x{W} -> {scene.gaussians.means.shape[1]} pixel-aligned Gaussians "
+            f"({cfg.scale_mode} scales, scale_max {cfg.scale_max}), {v} target views per GPU, fwd+bwd, colour")
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from my_depthsplat_b200 import _lib
+    from my_depthsplat_b200 import rasterizer as R
+    from my_depthsplat_b200.decoder_splatting_cuda import DecoderSplattingCUDACfg, get_decoder
+    from my_depthsplat_b200.scenes import CONFIGS, make_scene
+    from my_depthsplat_b200.types import Gaussians
+
+    L = _lib.load()
+    cfg = CONFIGS[args.config]
+    V = args.views or cfg.v_tgt
+    scene_cpu = make_scene(cfg, v_tgt=V * world)  # same seed on every rank -> identical (replicated) Gaussians
+    H, W = scene_cpu.image_shape
+    N = scene_cpu.gaussians.means.shape[1]
+    vs = slice(rank * V, (rank + 1) * V)  # this rank's shard of the target views
+    host = {
+        "means": scene_cpu.gaussians.means, "covariances": scene_cpu.gaussians.covariances,
+        "harmonics": scene_cpu.gaussians.harmonics, "opacities": scene_cpu.gaussians.opacities,
+        "extrinsics": scene_cpu.extrinsics[:, vs].contiguous(), "intrinsics": scene_cpu.intrinsics[:, vs].contiguous(),
+        "near": scene_cpu.near[:, vs].contiguous(), "far": scene_cpu.far[:, vs].contiguous(),
+        "grad_color": scene_cpu.grad_color[:, vs].contiguous(),
+    }
+    host = {k: v.pin_memory() for k, v in host.items()}
+    devt = {k: v.to(dev) for k, v in host.items()}
+    dataset_cfg = type("DatasetCfg", (), {"background_color": [0.0, 0.0, 0.0]})()
+    decoder = get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), dataset_cfg).to(dev)
+    gnames = ("means", "covariances", "harmonics", "opacities")
+
+    def step(t):
+        leaves = [t[k].detach().requires_grad_() for k in gnames]
+        out = decoder.forward(Gaussians(*leaves), t["extrinsics"], t["intrinsics"], t["near"], t["far"], (H, W), depth_mode=None)
+        grads = torch.autograd.grad(out.color, leaves, t["grad_color"])
+        if world > 1:  # view-sharded training: per-Gaussian gradients are summed over the ranks
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            grads = flat
+        return out.color, grads
+
+    host_out = {}
+
+    def step_e2e():
+        t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        color, grads = step(t)
+        outs = [color] + (list(grads) if isinstance(grads, (tuple, list)) else [grads])
+        for i, o in enumerate(outs):
+            if i not in host_out:
+                host_out[i] = torch.empty(o.shape, dtype=o.dtype, pin_memory=True)
+            host_out[i].copy_(o, non_blocking=True)
+        return outs
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.b200s_kernel_launches()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = L.b200s_kernel_launches() - l0
+        clocks = sampler.stop()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms, launches, clocks
+
+    W_ = max(args.warmup, 3)
+    ms, launches, clocks = timed(lambda: step(devt), args.steps, W_)
+    ms_step = ms / args.steps
+    pix_step = world * V * H * W
+    value = pix_step / (ms_step * 1e-3) / 1e6
+
+    ms_e, _, _ = timed(step_e2e, args.steps, 2)
+    ms_step_e = ms_e / args.steps
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    e2e_value = pix_step / (ms_step_e * 1e-3) / 1e6
+
+    # ---- per-stage device time (CUDA events recorded by the library on the launching stream) ----------
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    nprof = 5
+    torch.cuda.synchronize()
+    acc = {}
+    for _ in range(nprof):
+        step(devt)
+        for k, v in _lib.profile_read().items():
+            acc[k] = acc.get(k, 0.0) + v
+    _lib.profile_enable(False)
+    stages_ms = {k: v / nprof for k, v in acc.items()}
+
+    # ---- work counters of one forward (pairs, visible, tested, blended) --------------------------------
+    from my_depthsplat_b200.cuda_splatting import render_views
+    with torch.no_grad():
+        render_views(devt["extrinsics"], devt["intrinsics"], devt["near"], devt["far"], (H, W), decoder.background_color,
+                     devt["means"], devt["covariances"], devt["harmonics"], devt["opacities"], count_work=True)
+    st = R.last_stats
+    plan = _lib.plan(1, N, V, H, W, max(st.num_pairs, 1))
+
+    hbm_peak, sm_max, peak_src = _peaks()
+    sm_mhz = clocks["sm_mhz"] or sm_max
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the clock seen under load
+    Rn, Nv, P = st.num_pairs, st.num_visible, V * H * W
+    alg = {  # algorithmic bytes / flops per launch
+        "pre_bin": ("hbm", 148.0 * N * V + 64.0 * N * V + 12.0 * Rn),
+        "sort_hist": ("hbm", 8.0 * Rn),
+        "sort_passes": ("hbm", 24.0 * Rn * plan.sort_passes),
+        "ranges": ("hbm", 8.0 * Rn + 8.0 * plan.bins),
+        "comp_fwd": ("fp32", 15.0 * st.tested + 11.0 * st.blended),
+        "comp_bwd": ("fp32", 15.0 * st.tested + 63.0 * st.blended),
+        "pre_bwd": ("hbm", 296.0 * N + 64.0 * N * V),
+        "grad_zero": ("hbm", 48.0 * N * V),
+    }
+    stage_report = {}
+    for k, ms_k in stages_ms.items():
+        if k not in alg or ms_k <= 0:
+            continue
+        bound, amount = alg[k]
+        if bound == "hbm":
+            ach = amount / (ms_k * 1e-3) / 1e9
+            stage_report[k] = {"ms": round(ms_k, 4), "bound": "hbm", "achieved": round(ach, 1), "unit": "GB/s", "frac": round(ach / hbm_peak, 4)}
+        else:
+            ach = amount / (ms_k * 1e-3) / 1e12
+            stage_report[k] = {"ms": round(ms_k, 4), "bound": "fp32", "achieved": round(ach, 3), "unit": "TFLOP/s", "frac": round(ach / fp32_peak, 4)}
+    dom = max(stage_report, key=lambda k: stage_report[k]["ms"]) if stage_report else None
+    roofline = None
+    if dom:
+        r = stage_report[dom]
+        roofline = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": round(hbm_peak if r["bound"] == "hbm" else fp32_peak, 2),
+                    "unit": r["unit"], "frac": r["frac"], "traffic": None, "ms": r["ms"],
+                    "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs" if r["bound"] == "hbm" else
+                    f"148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock sampled under load)",
+                    "share_of_step": round(r["ms"] / max(sum(v["ms"] for v in stage_report.values()), 1e-9), 4)}
+    hbm_stages = {k: v for k, v in stage_report.items() if v["bound"] == "hbm"}
+    dom_hbm = max(hbm_stages, key=lambda k: hbm_stages[k]["ms"]) if hbm_stages else None
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        mpix, sec = time_oracle(make_scene(cfg, v_tgt=1), 2, 1, threads)
+        cpu_baseline = {"value": round(mpix, 4), "unit": "Mpix/s", "cores": threads, "kind": "port",
+                        "sample": f"1 of the {V} target views ({H}x{W}, all {N} Gaussians), fwd+bwd, mean of 2 runs, {sec:.2f} s each"}
+
+    if rank == 0:
+        line = {
+            "metric": "rasterizer fwd+bwd Mpix/s", "value": round(value, 2), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": W_, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": _workload_name(cfg, scene_cpu, V), "views_per_gpu": V, "gaussians": N, "height": H, "width": W,
+                       "l2": "inputs larger than L2 (Gaussians 472 MB + 64 B records per view)" if N * 160 > 126e6 else "inputs fit L2",
+                       "parallelism": f"view-sharded x{world}, Gaussians replicated" + (", NCCL all-reduce of per-Gaussian grads" if world > 1 else "")},
+            "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(ms_step_e, 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_hbm": ({"kernel": dom_hbm, **hbm_stages[dom_hbm], "peak": hbm_peak} if dom_hbm else None),
+            "stages": stage_report,
+            "work": {"pairs": Rn, "visible": Nv, "tested": st.tested, "blended": st.blended, "max_tile_len": st.max_tile_len,
+                     "sort_passes": plan.sort_passes, "pixels_per_step": pix_step},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2T")
+    ap.add_argument("--views", type=int, default=0, help="target views per GPU (default: the config's)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

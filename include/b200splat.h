@@ -177,6 +177,18 @@ size_t b200s_sort_tmp_bytes(int64_t n);
 int b200s_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, int32_t bits,
                      void* tmp, void* stream);
 
+/* Optional per-stage device timing (CUDA events recorded on the caller's stream at stage boundaries;
+ * off by default, process-wide).  bench.py uses it for the per-kernel roofline numbers. */
+enum { B200S_STAGE_PRE_BIN = 0, B200S_STAGE_SORT_HIST = 1, B200S_STAGE_SORT_PASSES = 2, B200S_STAGE_RANGES = 3,
+       B200S_STAGE_COMP_FWD = 4, B200S_STAGE_GRAD_ZERO = 5, B200S_STAGE_COMP_BWD = 6, B200S_STAGE_PRE_BWD = 7,
+       B200S_STAGE_END = 8, B200S_NUM_STAGES = 9 };
+void b200s_profile_enable(int on);
+/* Synchronises on the recorded events, ADDS the elapsed milliseconds of every stage recorded since the
+ * last read into ms_by_stage[B200S_NUM_STAGES], clears the recording.  Returns the number of stages seen. */
+int b200s_profile_read(float* ms_by_stage);
+/* Number of this library's kernels launched by the process so far (memsets not counted). */
+long long b200s_kernel_launches(void);
+
 int b200s_abi_version(void);
 int b200s_last_cuda_error(void);       /* cudaError_t of the last failed launch on this thread */
 const char* b200s_build_info(void);    /* "sm_100a nvcc <ver> ..." */

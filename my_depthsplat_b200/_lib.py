@@ -81,8 +81,10 @@ class GradIn(C.Structure):
 # every symbol include/b200splat.h declares (tests check the exports against this list)
 EXPORTS = (
     "b200s_plan", "b200s_forward_bin", "b200s_forward_render", "b200s_backward", "b200s_sort_tmp_bytes",
-    "b200s_sort_pairs", "b200s_abi_version", "b200s_last_cuda_error", "b200s_build_info",
+    "b200s_sort_pairs", "b200s_abi_version", "b200s_last_cuda_error", "b200s_build_info", "b200s_profile_enable",
+    "b200s_profile_read", "b200s_kernel_launches",
 )
+STAGES = ("pre_bin", "sort_hist", "sort_passes", "ranges", "comp_fwd", "grad_zero", "comp_bwd", "pre_bwd", "end")
 
 _lib = None
 
@@ -121,6 +123,11 @@ def load() -> C.CDLL:
     L.b200s_sort_tmp_bytes.argtypes = [C.c_int64]
     L.b200s_sort_pairs.restype = C.c_int
     L.b200s_sort_pairs.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
+    L.b200s_profile_enable.restype = None
+    L.b200s_profile_enable.argtypes = [C.c_int]
+    L.b200s_profile_read.restype = C.c_int
+    L.b200s_profile_read.argtypes = [P(C.c_float)]
+    L.b200s_kernel_launches.restype = C.c_longlong
     if L.b200s_abi_version() != ABI_VERSION:
         raise LibraryMissing(f"{LIB_PATH} has ABI {L.b200s_abi_version()}, expected {ABI_VERSION}; rebuild it")
     _lib = L
@@ -142,3 +149,14 @@ def plan(num_scenes: int, num_gaussians: int, num_views: int, height: int, width
     p = Plan()
     check(load().b200s_plan(C.byref(d), C.byref(p)), "b200s_plan")
     return p
+
+
+def profile_enable(on: bool) -> None:
+    load().b200s_profile_enable(1 if on else 0)
+
+
+def profile_read() -> dict:
+    """Milliseconds per stage accumulated since the last read (synchronises on the recorded events)."""
+    buf = (C.c_float * len(STAGES))()
+    load().b200s_profile_read(buf)
+    return {name: float(buf[i]) for i, name in enumerate(STAGES) if name != "end"}

@@ -4,12 +4,36 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "kernels.cuh"
 
 
 using namespace b200s;
 
 static thread_local int g_last_cuda_error = 0;
+
+// ---- optional stage timing ---------------------------------------------------------------------------
+// Process-wide (forward runs on the caller's thread, backward on autograd's): guarded by a mutex, and
+// only touched at all when profiling is on.  The launch counter is a relaxed atomic.
+static std::atomic<bool> g_prof{false};
+static std::mutex g_prof_mu;
+static cudaEvent_t g_ev[64];
+static int g_ev_stage[64];
+static int g_nev = 0;
+static std::atomic<long long> g_launches{0};
+namespace b200s {
+void stage_mark(int stage, cudaStream_t stream) {
+  if (!g_prof.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (g_nev >= 64) return;
+  if (!g_ev[g_nev] && cudaEventCreate(&g_ev[g_nev]) != cudaSuccess) return;
+  cudaEventRecord(g_ev[g_nev], stream);
+  g_ev_stage[g_nev++] = stage;
+}
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace b200s
 
 static int fail(cudaError_t e) {
   g_last_cuda_error = (int)e;
@@ -29,6 +53,23 @@ static int bits_for(int n) { int b = 0; while ((1 << b) < n) b++; return b; }
 extern "C" {
 
 int b200s_abi_version(void) { return B200S_ABI_VERSION; }
+void b200s_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.store(on != 0);
+  g_nev = 0;
+}
+int b200s_profile_read(float* ms) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  int seen = 0;
+  if (g_nev > 0) cudaEventSynchronize(g_ev[g_nev - 1]);
+  for (int i = 0; i + 1 < g_nev; i++) {
+    float t = 0.f;
+    if (g_ev_stage[i] != B200S_STAGE_END && cudaEventElapsedTime(&t, g_ev[i], g_ev[i + 1]) == cudaSuccess) { ms[g_ev_stage[i]] += t; seen++; }
+  }
+  g_nev = 0;
+  return seen;
+}
+long long b200s_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 int b200s_last_cuda_error(void) { return g_last_cuda_error; }
 const char* b200s_build_info(void) {
 #define B200S_STR2(x) #x
@@ -143,6 +184,7 @@ int b200s_forward_render(const B200sScene* sc, const B200sViews* vw, const B200s
   a.n_contrib = reinterpret_cast<uint32_t*>(saved + pl->off_n_contrib);
   a.status = st;
   e = launch_composite_fwd(a, pl->tiles, vw->num_views, vw->depth_mode != B200S_DEPTH_NONE, out->count_work != 0, stream);
+  stage_mark(B200S_STAGE_END, stream);
   return e == cudaSuccess ? B200S_OK : fail(e);
 }
 
@@ -158,6 +200,7 @@ int b200s_backward(const B200sScene* sc, const B200sViews* vw, const B200sPlan* 
   cudaStream_t stream = (cudaStream_t)stream_;
   const B200sStatus* st = reinterpret_cast<const B200sStatus*>(saved + pl->off_status);
   float* grad_rec = reinterpret_cast<float*>(scratch + pl->off_grad_rec);
+  stage_mark(B200S_STAGE_GRAD_ZERO, stream);
   cudaError_t e = cudaMemsetAsync(grad_rec, 0, (size_t)vw->num_views * sc->num_gaussians * GREC_FLOATS * sizeof(float), stream);
   if (e != cudaSuccess) return fail(e);
   CompArgs a;
@@ -173,6 +216,7 @@ int b200s_backward(const B200sScene* sc, const B200sViews* vw, const B200sPlan* 
   e = launch_composite_bwd(a, pl->tiles, vw->num_views, vw->depth_mode != B200S_DEPTH_NONE, stream);
   if (e != cudaSuccess) return fail(e);
   e = launch_preprocess_bwd(*sc, *vw, *pl, saved, scratch, *gin, stream);
+  stage_mark(B200S_STAGE_END, stream);
   return e == cudaSuccess ? B200S_OK : fail(e);
 }
 

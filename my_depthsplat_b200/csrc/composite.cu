@@ -280,6 +280,8 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(const CompArgs 
 cudaError_t launch_composite_fwd(const CompArgs& a, int tiles, int views, bool depth, bool count, cudaStream_t stream) {
   if (tiles <= 0 || views <= 0) return cudaSuccess;
   dim3 grid(tiles, views);
+  stage_mark(B200S_STAGE_COMP_FWD, stream);
+  count_launches(1);
   if (depth) { if (count) composite_fwd_kernel<true, true><<<grid, TILE_PIX, 0, stream>>>(a); else composite_fwd_kernel<true, false><<<grid, TILE_PIX, 0, stream>>>(a); }
   else { if (count) composite_fwd_kernel<false, true><<<grid, TILE_PIX, 0, stream>>>(a); else composite_fwd_kernel<false, false><<<grid, TILE_PIX, 0, stream>>>(a); }
   return cudaGetLastError();
@@ -287,6 +289,8 @@ cudaError_t launch_composite_fwd(const CompArgs& a, int tiles, int views, bool d
 cudaError_t launch_composite_bwd(const CompArgs& a, int tiles, int views, bool depth, cudaStream_t stream) {
   if (tiles <= 0 || views <= 0) return cudaSuccess;
   dim3 grid(tiles, views);
+  stage_mark(B200S_STAGE_COMP_BWD, stream);
+  count_launches(1);
   if (depth) composite_bwd_kernel<true><<<grid, TILE_PIX, 0, stream>>>(a);
   else composite_bwd_kernel<false><<<grid, TILE_PIX, 0, stream>>>(a);
   return cudaGetLastError();

@@ -30,6 +30,10 @@ struct CompArgs {
   float* grad_rec;         // [VV,N,12]
 };
 
+// profiling hooks implemented in api.cu (no-ops unless b200s_profile_enable(1))
+void stage_mark(int stage, cudaStream_t stream);
+void count_launches(int n);
+
 cudaError_t launch_preprocess_bin(const B200sScene&, const B200sViews&, const B200sPlan&, char* saved, char* scratch, const B200sOut*,
                                   cudaStream_t);
 size_t sort_tmp_bytes(long long n_cap);

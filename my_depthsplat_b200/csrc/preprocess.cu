@@ -304,6 +304,7 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   a.radii = out ? out->radii : nullptr;
 
   cudaError_t e;
+  stage_mark(B200S_STAGE_PRE_BIN, stream);
   if ((e = cudaMemsetAsync(a.status, 0, sizeof(B200sStatus), stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(a.counters, 0, CNT_WORDS * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(a.scan_state, 0, (size_t)plan.pre_tickets * sizeof(uint64_t), stream)) != cudaSuccess) return e;
@@ -314,7 +315,7 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
     if ((e = cudaFuncSetAttribute(preprocess_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     configured = smem;
   }
-  if (plan.pre_tickets > 0) preprocess_bin_kernel<<<plan.pre_tickets, PRE_THREADS, smem, stream>>>(sc, vw, a);
+  if (plan.pre_tickets > 0) { preprocess_bin_kernel<<<plan.pre_tickets, PRE_THREADS, smem, stream>>>(sc, vw, a); count_launches(1); }
   return cudaGetLastError();
 }
 }  // namespace b200s

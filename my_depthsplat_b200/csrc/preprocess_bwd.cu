@@ -281,6 +281,8 @@ cudaError_t launch_preprocess_bwd(const B200sScene& sc, const B200sViews& vw, co
   const size_t smem = (size_t)PRE_THREADS * (3 + a.cov_floats + a.col_stride) * sizeof(float);
   const int nc = sc.colors_precomp ? 0 : (sc.sh_degree + 1) * (sc.sh_degree + 1);
   cudaError_t e = cudaSuccess;
+  stage_mark(B200S_STAGE_PRE_BWD, stream);
+  count_launches(1);
 #define LAUNCH(NCV)                                                                                                        \
   {                                                                                                                        \
     e = cudaFuncSetAttribute(preprocess_bwd_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \

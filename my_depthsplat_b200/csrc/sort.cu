@@ -270,9 +270,12 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     const long long max_blocks = (long long)sm_count * 4;
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
+    stage_mark(B200S_STAGE_SORT_HIST, stream);
     digit_histogram_kernel<<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
     digit_scan_kernel<<<1, RADIX, 0, stream>>>(hist, passes);
+    count_launches(2);
   }
+  stage_mark(B200S_STAGE_SORT_PASSES, stream);
   for (int p = 0; p < passes; p++) {
     PassArgs a;
     a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout;
@@ -282,6 +285,7 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     a.tile_counter = counters + CNT_SORT_TILE0 + p;
     a.cnt = cnt; a.shift = 8 * p;
     onesweep_pass_kernel<<<tiles - 1 > 0 ? tiles - 1 : 1, SORT_THREADS, 0, stream>>>(a);
+    count_launches(1);
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
@@ -295,7 +299,9 @@ cudaError_t launch_tile_ranges(const uint64_t* keys, CountRef cnt, uint2* ranges
   const long long max_blocks = (long long)sm_count * 8;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
+  stage_mark(B200S_STAGE_RANGES, stream);
   tile_ranges_kernel<<<(int)blocks, 256, 0, stream>>>(keys, cnt, ranges);
+  count_launches(1);
   return cudaGetLastError();
 }
 

@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
         L.orc_forward.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32]
         L.orc_backward.restype = None
         L.orc_backward.argtypes = [vp] * 13
+        L.orc_set_parallel_backward.restype = None
+        L.orc_set_parallel_backward.argtypes = [i32]
         L.orc_free.restype = None
         L.orc_free.argtypes = [vp]
         for name in ("orc_num_rendered", "orc_tested", "orc_blended"):
@@ -123,8 +125,9 @@ def forward_view(*, H, W, bg, means3D, opacities, cov3D, viewmatrix, projmatrix,
     P = means3D.shape[0]
     M = 0
     if shs is not None:
-        shs = _f32(shs).reshape(P, -1, 3)
-        M = shs.shape[1]
+        shs = _f32(shs)
+        M = shs.shape[-2]
+        shs = shs.reshape(P, M, 3)
         assert (sh_degree + 1) ** 2 <= M
     else:
         colors_precomp = _f32(colors_precomp).reshape(P, 3)
@@ -152,6 +155,11 @@ def backward_view(st: ViewState, dL_dpix) -> dict:
     if M == 0:
         out["sh"] = None
     return out
+
+
+def set_parallel_backward(on: bool) -> None:
+    """OpenMP + atomic adds in the compositing backward (timing only; the parity tests use the serial order)."""
+    lib().orc_set_parallel_backward(1 if on else 0)
 
 
 def set_threads(n: int | None):
