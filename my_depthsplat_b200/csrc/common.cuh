@@ -39,7 +39,7 @@ __device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
                                        -0.5900435899266435f};
 
 // ---- projected record: 64 bytes per (view, Gaussian), written by preprocess ---------------------
-// q0 = (x, y, conicA, conicB)   q1 = (conicC, opacity, r, g)   q2 = (b, zc, ex, ey)
+// q0 = (x, y, ex, ey) [cull record]   q1 = (conicA, conicB, conicC, opacity)   q2 = (r, g, b, zc)
 // q3 = (depth, radius:int, rect packed u32 [minx | miny<<8 | maxx<<16 | maxy<<24], flags:u32)
 // Compositing reads q0..q2 (48 B); q3 is for the backward preprocess, radii output and tests.
 // (ex, ey) is the conservative half-extent of the alpha >= 1/255 region, used for sub-tile culling;

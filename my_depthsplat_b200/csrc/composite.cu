@@ -1,15 +1,22 @@
 // composite.cu -- 16x16-tile alpha compositing, forward and backward.
 //
-// One CTA of 256 threads per (view, tile); thread = pixel.  Each warp owns an 8x4-pixel sub-tile.
-// The tile's depth-sorted list is staged 256 entries at a time into shared memory (48 B projected
-// record per entry, gathered by Gaussian index).  Before a warp evaluates an entry on its 32 pixels,
-// ONE lane tests that entry's alpha>=1/255 extent against the warp's sub-tile (32 entries tested per
-// instruction, warp ballot), so a warp only walks the entries that can touch it; the ballot also
-// gives warp-level early termination.  Results are identical to walking the whole list: a skipped
-// entry is one whose alpha is below 1/255 on every pixel of the sub-tile.
+// One CTA of 256 threads per (view, tile); thread = pixel; each WARP owns an 8x4-pixel sub-tile and
+// walks the tile's depth-sorted list ON ITS OWN -- there is no block-wide staging and no
+// __syncthreads in the list loop, so a warp whose pixels saturate early (or whose sub-tile few
+// Gaussians touch) never waits for the other seven.  Per 32 list entries a warp
+//   1. loads the 32 Gaussian indices (coalesced) and each lane gathers ONE 16-byte cull record
+//      (x, y, ex, ey) -- the eight warps of the CTA read the same lines, so seven of them hit L1;
+//   2. tests its entry's alpha>=1/255 extent against the warp's sub-tile (32 entries per instruction)
+//      and ballots;
+//   3. the hit lanes gather the remaining 32 bytes of their record and compact (q0,q1,q2) into the
+//      warp's private shared-memory slots;
+//   4. all lanes evaluate the compacted hits on their pixels, reading the slots by broadcast.
+// Indices and cull records are software-prefetched two / one chunks ahead.  Results are identical to
+// walking the whole list: a skipped entry is one whose alpha is below 1/255 on every pixel of the
+// sub-tile.
 //
 // Forward composites RGB and the depth colour in the same pass (the reference renders twice,
-// cuda_splatting.py:250-263).  Backward replays the list back to front; per-pixel gradient
+// cuda_splatting.py:250-263).  Backward replays the list back to front; the per-pixel gradient
 // contributions of three entries at a time are summed across the warp with a 31-shuffle
 // reduce-scatter butterfly (instead of 5 shuffles per value), leaving one value per lane, which is
 // added to the per-(view,Gaussian) gradient record with a single RED per lane.
@@ -19,6 +26,7 @@
 
 namespace b200s {
 
+constexpr int WARPS = TILE_PIX / 32;
 
 struct TileGeom {
   int px, py;
@@ -36,69 +44,81 @@ __device__ __forceinline__ TileGeom tile_geom(int tile, int grid_x, int H, int W
   g.X0 = (float)x0; g.X1 = (float)(x0 + 7); g.Y0 = (float)y0; g.Y1 = (float)(y0 + 3);
   return g;
 }
-__device__ __forceinline__ bool subtile_hit(const float4 q0, const float ex, const float ey, const TileGeom& g) {
-  return (q0.x + ex >= g.X0) && (q0.x - ex <= g.X1) && (q0.y + ey >= g.Y0) && (q0.y - ey <= g.Y1);
+// q0 = (x, y, ex, ey)
+__device__ __forceinline__ bool subtile_hit(const float4 q0, const TileGeom& g) {
+  return (q0.x + q0.z >= g.X0) && (q0.x - q0.z <= g.X1) && (q0.y + q0.w >= g.Y0) && (q0.y - q0.w <= g.Y1);
 }
 
 // -------------------------------------------------------------------------------------------------
 template <bool DEPTH, bool COUNT>
 __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs a) {
-  __shared__ float4 s_q0[TILE_PIX], s_q1[TILE_PIX], s_q2[TILE_PIX];
+  __shared__ float4 s_q0[WARPS][32], s_q1[WARPS][32], s_q2[WARPS][32];
+  __shared__ uint32_t s_pos[WARPS][32];
   if (*a.overflow) return;
   const int tile = blockIdx.x, view = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
   const uint2 range = a.ranges[((uint32_t)view << a.tile_bits) | (uint32_t)tile];
   const TileGeom g = tile_geom(tile, a.grid_x, a.H, a.W);
   const Rec* __restrict__ vrec = a.rec + (size_t)view * a.N;
+  const uint32_t* __restrict__ list = a.vals + range.x;
+  const uint32_t len = range.y - range.x;
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
   uint32_t last = 0, nblend = 0;
   bool done = !g.inside;
-  bool warp_done = __all_sync(0xffffffffu, done);
 
-  for (uint32_t base = range.x; base < range.y; base += TILE_PIX) {
-    if (__syncthreads_count(done) == TILE_PIX) break;
-    const int nst = min((uint32_t)TILE_PIX, range.y - base);
-    if (tid < nst) {
-      const uint32_t id = __ldg(a.vals + base + tid);
-      const float4* r = reinterpret_cast<const float4*>(vrec + id);
-      s_q0[tid] = __ldg(r); s_q1[tid] = __ldg(r + 1); s_q2[tid] = __ldg(r + 2);
-    }
-    __syncthreads();
-    if (warp_done) continue;
-    for (int c = 0; c < nst; c += 32) {
-      const int j = c + lane;
-      bool hit = false;
-      if (j < nst) { const float4 q2 = s_q2[j]; hit = subtile_hit(s_q0[j], q2.z, q2.w, g); }
-      uint32_t mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {
-        const int jj = c + __ffs(mask) - 1;
-        mask &= mask - 1;
+  if (!__all_sync(0xffffffffu, done)) {
+    // software pipeline: indices two chunks ahead, cull records one chunk ahead
+    uint32_t id_cur = lane < len ? __ldg(list + lane) : 0u;
+    uint32_t id_nxt = 32 + lane < len ? __ldg(list + 32 + lane) : 0u;
+    float4 q0_cur = lane < len ? __ldg(&vrec[id_cur].q0) : make_float4(0.f, 0.f, -1.f, -1.f);
+    for (uint32_t base = 0; base < len; base += 32) {
+      const uint32_t id = id_cur;
+      const float4 q0 = q0_cur;
+      const bool valid = base + lane < len;
+      id_cur = id_nxt;
+      id_nxt = base + 64 + lane < len ? __ldg(list + base + 64 + lane) : 0u;
+      q0_cur = base + 32 + lane < len ? __ldg(&vrec[id_cur].q0) : make_float4(0.f, 0.f, -1.f, -1.f);
+
+      const bool hit = valid && subtile_hit(q0, g);
+      const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      if (mask == 0) continue;
+      if (hit) {
+        const int slot = __popc(mask & lt);
+        const float4* r = reinterpret_cast<const float4*>(vrec + id);
+        s_q0[warp][slot] = q0; s_q1[warp][slot] = __ldg(r + 1); s_q2[warp][slot] = __ldg(r + 2);
+        s_pos[warp][slot] = base + lane + 1u;
+      }
+      __syncwarp();
+      const int nh = __popc(mask);
+      for (int k = 0; k < nh; k++) {
         if (!done) {
-          const float4 q0 = s_q0[jj], q1 = s_q1[jj];
-          const float dx = __fsub_rn(q0.x, g.pfx), dy = __fsub_rn(q0.y, g.pfy);
-          const float power = gauss_power(q0.z, q0.w, q1.x, dx, dy);
+          const float4 h0 = s_q0[warp][k], h1 = s_q1[warp][k];
+          const float dx = __fsub_rn(h0.x, g.pfx), dy = __fsub_rn(h0.y, g.pfy);
+          const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
           if (power <= 0.0f) {
-            const float alpha = fminf(ALPHA_MAX, __fmul_rn(q1.y, expf(power)));
+            const float alpha = fminf(ALPHA_MAX, __fmul_rn(h1.w, expf(power)));
             if (alpha >= ALPHA_MIN) {
               const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
               if (test_T < T_MIN) {
                 done = true;
               } else {
-                const float4 q2 = s_q2[jj];
-                C0 = __fmaf_rn(__fmul_rn(q1.z, alpha), T, C0);
-                C1 = __fmaf_rn(__fmul_rn(q1.w, alpha), T, C1);
-                C2 = __fmaf_rn(__fmul_rn(q2.x, alpha), T, C2);
-                if (DEPTH) D = __fmaf_rn(__fmul_rn(q2.y, alpha), T, D);
+                const float4 h2 = s_q2[warp][k];
+                C0 = __fmaf_rn(__fmul_rn(h2.x, alpha), T, C0);
+                C1 = __fmaf_rn(__fmul_rn(h2.y, alpha), T, C1);
+                C2 = __fmaf_rn(__fmul_rn(h2.z, alpha), T, C2);
+                if (DEPTH) D = __fmaf_rn(__fmul_rn(h2.w, alpha), T, D);
                 T = test_T;
-                last = base - range.x + (uint32_t)jj + 1u;
+                last = s_pos[warp][k];
                 if (COUNT) nblend++;
               }
             }
           }
         }
       }
-      if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
+      __syncwarp();  // this chunk's slot reads are done before the next chunk overwrites the slots
+      if (__all_sync(0xffffffffu, done)) break;
     }
   }
   if (g.inside) {
@@ -120,7 +140,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs 
     if (lane == 0) {
       atomicAdd((unsigned long long*)&a.status->tested, t);
       atomicAdd((unsigned long long*)&a.status->blended, b);
-      if (tid == 0) atomicMax(&a.status->max_tile_len, range.y - range.x);
+      if (threadIdx.x == 0) atomicMax(&a.status->max_tile_len, len);
     }
   }
 }
@@ -147,21 +167,22 @@ struct PixState {
 };
 
 // one list entry on one pixel; writes its 10 partial gradients to out[0..9]
+// h0 = (x, y, ex, ey)  h1 = (A, B, C, opacity)  h2 = (r, g, b, zc)
 template <bool DEPTH>
-__device__ __forceinline__ void bwd_entry(const float4 q0, const float4 q1, const float4 q2, const uint32_t pos, PixState<DEPTH>& s,
+__device__ __forceinline__ void bwd_entry(const float4 h0, const float4 h1, const float4 h2, const uint32_t pos, PixState<DEPTH>& s,
                                           const TileGeom& g, const float half_w, const float half_h, float* out) {
 #pragma unroll
   for (int k = 0; k < 10; k++) out[k] = 0.f;
   if (pos >= s.last_contributor) return;
-  const float dx = __fsub_rn(q0.x, g.pfx), dy = __fsub_rn(q0.y, g.pfy);
-  const float power = gauss_power(q0.z, q0.w, q1.x, dx, dy);
+  const float dx = __fsub_rn(h0.x, g.pfx), dy = __fsub_rn(h0.y, g.pfy);
+  const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
   if (power > 0.0f) return;
   const float G = expf(power);
-  const float alpha = fminf(ALPHA_MAX, __fmul_rn(q1.y, G));
+  const float alpha = fminf(ALPHA_MAX, __fmul_rn(h1.w, G));
   if (alpha < ALPHA_MIN) return;
   s.T = s.T / (1.f - alpha);
   const float w = alpha * s.T;
-  const float col[4] = {q1.z, q1.w, q2.x, q2.y};
+  const float col[4] = {h2.x, h2.y, h2.z, h2.w};
   float dL_dalpha = 0.f;
 #pragma unroll
   for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) {
@@ -173,10 +194,10 @@ __device__ __forceinline__ void bwd_entry(const float4 q0, const float4 q1, cons
   dL_dalpha *= s.T;
   s.last_alpha = alpha;
   dL_dalpha += (-s.T_final / (1.f - alpha)) * s.bg_dot;
-  const float dL_dG = q1.y * dL_dalpha;
+  const float dL_dG = h1.w * dL_dalpha;
   const float gdx = G * dx, gdy = G * dy;
-  const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
-  const float dG_ddely = -gdy * q1.x - gdx * q0.w;
+  const float dG_ddelx = -gdx * h1.x - gdy * h1.y;
+  const float dG_ddely = -gdy * h1.z - gdx * h1.y;
   out[0] = dL_dG * dG_ddelx * half_w;
   out[1] = dL_dG * dG_ddely * half_h;
   out[2] = -0.5f * gdx * dx * dL_dG;
@@ -186,17 +207,18 @@ __device__ __forceinline__ void bwd_entry(const float4 q0, const float4 q1, cons
 }
 
 template <bool DEPTH>
-__global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(const CompArgs a) {
-  __shared__ float4 s_q0[TILE_PIX], s_q1[TILE_PIX], s_q2[TILE_PIX];
-  __shared__ uint32_t s_id[TILE_PIX];
-  __shared__ uint32_t s_max[TILE_PIX / 32];
+__global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_kernel(const CompArgs a) {
+  __shared__ float4 s_q0[WARPS][32], s_q1[WARPS][32], s_q2[WARPS][32];
+  __shared__ uint32_t s_pos[WARPS][32], s_id[WARPS][32];
   if (*a.overflow) return;
   const int tile = blockIdx.x, view = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
   const uint2 range = a.ranges[((uint32_t)view << a.tile_bits) | (uint32_t)tile];
   if (range.y == range.x) return;
   const TileGeom g = tile_geom(tile, a.grid_x, a.H, a.W);
   const Rec* __restrict__ vrec = a.rec + (size_t)view * a.N;
+  const uint32_t* __restrict__ list = a.vals + range.x;
   float* __restrict__ grec = a.grad_rec + (size_t)view * a.N * GREC_FLOATS;
   const size_t HW = (size_t)a.H * a.W;
   const size_t pid = (size_t)g.py * a.W + g.px;
@@ -217,62 +239,60 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(const CompArgs 
     }
     if (DEPTH) s.dpix[3] = a.dL_ddepth[(size_t)view * HW + pid];
   }
-  // entries at list positions >= max(last_contributor) are needed by nobody
+  // entries at list positions >= the warp's max(last_contributor) are needed by none of its pixels
   uint32_t wmax = s.last_contributor;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
-  if (lane == 0) s_max[warp] = wmax;
-  __syncthreads();
-  uint32_t bmax = 0;
-#pragma unroll
-  for (int w = 0; w < TILE_PIX / 32; w++) bmax = max(bmax, s_max[w]);
+  if (wmax == 0) return;
   const float half_w = 0.5f * (float)a.W, half_h = 0.5f * (float)a.H;
 
-  for (uint32_t hi = bmax; hi > 0;) {
-    const uint32_t nst = min(hi, (uint32_t)TILE_PIX);
-    __syncthreads();  // previous round fully consumed
-    if ((uint32_t)tid < nst) {
-      // slot `tid` holds list position hi-1-tid: slots ascend as the list is walked back to front
-      const uint32_t id = __ldg(a.vals + range.x + (hi - 1 - tid));
+  // walk positions wmax-1 ... 0; lane l of a chunk starting at `top` holds position top-1-l, so that the
+  // compacted slots ascend as the list is walked back to front
+  int top = (int)wmax;
+  uint32_t id_cur = top - 1 - lane >= 0 ? __ldg(list + (top - 1 - lane)) : 0u;
+  uint32_t id_nxt = top - 33 - lane >= 0 ? __ldg(list + (top - 33 - lane)) : 0u;
+  float4 q0_cur = top - 1 - lane >= 0 ? __ldg(&vrec[id_cur].q0) : make_float4(0.f, 0.f, -1.f, -1.f);
+  for (; top > 0; top -= 32) {
+    const uint32_t id = id_cur;
+    const float4 q0 = q0_cur;
+    const int pos = top - 1 - lane;
+    id_cur = id_nxt;
+    id_nxt = top - 65 - lane >= 0 ? __ldg(list + (top - 65 - lane)) : 0u;
+    q0_cur = top - 33 - lane >= 0 ? __ldg(&vrec[id_cur].q0) : make_float4(0.f, 0.f, -1.f, -1.f);
+
+    const bool hit = pos >= 0 && subtile_hit(q0, g);
+    const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+    if (mask == 0) continue;
+    if (hit) {
+      const int slot = __popc(mask & lt);
       const float4* r = reinterpret_cast<const float4*>(vrec + id);
-      s_id[tid] = id; s_q0[tid] = __ldg(r); s_q1[tid] = __ldg(r + 1); s_q2[tid] = __ldg(r + 2);
+      s_q0[warp][slot] = q0; s_q1[warp][slot] = __ldg(r + 1); s_q2[warp][slot] = __ldg(r + 2);
+      s_pos[warp][slot] = (uint32_t)pos; s_id[warp][slot] = id;
     }
-    __syncthreads();
-    if (hi - nst < wmax) {  // warp-uniform: some pixel of this warp still needs entries of this round
-      for (uint32_t c = 0; c < nst; c += 32) {
-        const uint32_t j = c + lane;
-        bool hit = false;
-        if (j < nst && (hi - 1 - j) < wmax) { const float4 q2 = s_q2[j]; hit = subtile_hit(s_q0[j], q2.z, q2.w, g); }
-        uint32_t mask = __ballot_sync(0xffffffffu, hit);
-        while (mask) {
-          float v[32];
-          uint32_t ids[3];
-          bool used[3];
+    __syncwarp();
+    const int nh = __popc(mask);
+    for (int k0 = 0; k0 < nh; k0 += 3) {
+      float v[32];
+      uint32_t ids[3];
 #pragma unroll
-          for (int e = 0; e < 3; e++) {
-            used[e] = mask != 0;  // warp-uniform
-            if (used[e]) {
-              const uint32_t jj = c + __ffs(mask) - 1;
-              mask &= mask - 1;
-              ids[e] = s_id[jj];
-              bwd_entry<DEPTH>(s_q0[jj], s_q1[jj], s_q2[jj], hi - 1 - jj, s, g, half_w, half_h, v + 10 * e);
-            } else {
-              ids[e] = 0;
+      for (int e = 0; e < 3; e++) {
+        if (k0 + e < nh) {  // warp-uniform
+          ids[e] = s_id[warp][k0 + e];
+          bwd_entry<DEPTH>(s_q0[warp][k0 + e], s_q1[warp][k0 + e], s_q2[warp][k0 + e], s_pos[warp][k0 + e], s, g, half_w, half_h, v + 10 * e);
+        } else {
+          ids[e] = 0xffffffffu;
 #pragma unroll
-              for (int k = 0; k < 10; k++) v[10 * e + k] = 0.f;
-            }
-          }
-          v[30] = 0.f; v[31] = 0.f;
-          butterfly_step<16>(v, lane); butterfly_step<8>(v, lane); butterfly_step<4>(v, lane);
-          butterfly_step<2>(v, lane); butterfly_step<1>(v, lane);
-          const int e = lane / 10, k = lane - 10 * e;
-          const bool live = e == 0 ? used[0] : (e == 1 ? used[1] : (e == 2 ? used[2] : false));
-          const uint32_t id = e == 0 ? ids[0] : (e == 1 ? ids[1] : ids[2]);
-          if (live && v[0] != 0.f && (DEPTH || k != 9)) atomicAdd(grec + (size_t)id * GREC_FLOATS + k, v[0]);
+          for (int k = 0; k < 10; k++) v[10 * e + k] = 0.f;
         }
       }
+      v[30] = 0.f; v[31] = 0.f;
+      butterfly_step<16>(v, lane); butterfly_step<8>(v, lane); butterfly_step<4>(v, lane);
+      butterfly_step<2>(v, lane); butterfly_step<1>(v, lane);
+      const int e = lane / 10, k = lane - 10 * e;
+      const uint32_t gid = e == 0 ? ids[0] : (e == 1 ? ids[1] : (e == 2 ? ids[2] : 0xffffffffu));
+      if (gid != 0xffffffffu && v[0] != 0.f) atomicAdd(grec + (size_t)gid * GREC_FLOATS + k, v[0]);
     }
-    hi -= nst;
+    __syncwarp();  // slot reads of this chunk are done before the next chunk overwrites them
   }
 }
 

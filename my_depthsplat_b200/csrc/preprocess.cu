@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_bin_kernel(const B200s
 
   // ---- per-Gaussian projection ---------------------------------------------------------------
   Rec out;
-  out.q0 = make_float4(0.f, 0.f, 0.f, 0.f); out.q1 = out.q0; out.q2 = make_float4(0.f, 0.f, -1.f, -1.f); out.q3 = out.q0;
+  out.q0 = make_float4(0.f, 0.f, -1e30f, -1e30f); out.q1 = make_float4(0.f, 0.f, 0.f, 0.f); out.q2 = out.q1; out.q3 = out.q1;
   uint32_t tiles = 0;
   int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
   float depth = 0.f;
@@ -172,16 +172,16 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_bin_kernel(const B200s
             else zc = logf(fmaxf(fminf(z, vp.dnear), vp.dfar));
           }
           // conservative half-extents of the region where alpha can reach 1/255
-          float ex = -1.f, ey = -1.f;
+          float ex = -1e30f, ey = -1e30f;  // never reaches alpha >= 1/255: fails every sub-tile test
           const float o255 = 255.0f * opac;
           if (o255 >= 1.0f) {
             const float tau2 = 2.0f * logf(o255);
             ex = sqrtf(tau2 * q.a) * 1.01f + 0.1f;
             ey = sqrtf(tau2 * q.c) * 1.01f + 0.1f;
           }
-          out.q0 = make_float4(px, py, __fmul_rn(q.c, det_inv), __fmul_rn(-q.b, det_inv));
-          out.q1 = make_float4(__fmul_rn(q.a, det_inv), opac, rgb[0], rgb[1]);
-          out.q2 = make_float4(rgb[2], zc, ex, ey);
+          out.q0 = make_float4(px, py, ex, ey);
+          out.q1 = make_float4(__fmul_rn(q.c, det_inv), __fmul_rn(-q.b, det_inv), __fmul_rn(q.a, det_inv), opac);
+          out.q2 = make_float4(rgb[0], rgb[1], rgb[2], zc);
           const uint32_t rect = (uint32_t)rx0 | ((uint32_t)ry0 << 8) | ((uint32_t)rx1 << 16) | ((uint32_t)ry1 << 24);
           out.q3 = make_float4(depth, __int_as_float(radius), __uint_as_float(rect), __uint_as_float(flags));
         }

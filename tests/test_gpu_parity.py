@@ -128,8 +128,8 @@ def test_stage_outputs_bit_exact(name):
             np.testing.assert_array_equal(rec[vis, 13].view(np.int32), st.radii[vis])
             np.testing.assert_array_equal(rec[vis, 12].view(np.uint32), st.depths[vis].view(np.uint32))
             np.testing.assert_array_equal(rec[vis, 0:2].view(np.uint32), st.xy[vis].view(np.uint32))
-            np.testing.assert_array_equal(rec[vis, 2:5].view(np.uint32), st.conic_opacity[vis, 0:3][:, [0, 1, 2]].view(np.uint32))
-            np.testing.assert_allclose(rec[vis, 6:9], st.rgb[vis], atol=2e-6)
+            np.testing.assert_array_equal(rec[vis, 4:7].view(np.uint32), st.conic_opacity[vis, 0:3][:, [0, 1, 2]].view(np.uint32))
+            np.testing.assert_allclose(rec[vis, 8:11], st.rgb[vis], atol=2e-6)
             # this view's slice of the globally sorted list
             hi = (d["keys"] >> np.uint64(32))
             sel = (hi >> np.uint64(plan.tile_bits)) == np.uint64(vi)
