@@ -189,6 +189,10 @@ int b200s_profile_read(float* ms_by_stage);
 /* Number of this library's kernels launched by the process so far (memsets not counted). */
 long long b200s_kernel_launches(void);
 
+/* Tuning knobs for A/B measurements (not part of the stable contract): which 0 = digit-histogram variant
+ * (0 ballots, 1 MATCH.ANY, 2 shared atomics), which 1 = ranking variant (0 ballots, 1 MATCH.ANY, 2 alternating). */
+void b200s_debug_set(int which, int value);
+
 int b200s_abi_version(void);
 int b200s_last_cuda_error(void);       /* cudaError_t of the last failed launch on this thread */
 const char* b200s_build_info(void);    /* "sm_100a nvcc <ver> ..." */

@@ -82,7 +82,7 @@ class GradIn(C.Structure):
 EXPORTS = (
     "b200s_plan", "b200s_forward_bin", "b200s_forward_render", "b200s_backward", "b200s_sort_tmp_bytes",
     "b200s_sort_pairs", "b200s_abi_version", "b200s_last_cuda_error", "b200s_build_info", "b200s_profile_enable",
-    "b200s_profile_read", "b200s_kernel_launches",
+    "b200s_profile_read", "b200s_kernel_launches", "b200s_debug_set",
 )
 STAGES = ("pre_bin", "sort_hist", "sort_passes", "ranges", "comp_fwd", "grad_zero", "comp_bwd", "pre_bwd", "end")
 
@@ -128,6 +128,8 @@ def load() -> C.CDLL:
     L.b200s_profile_read.restype = C.c_int
     L.b200s_profile_read.argtypes = [P(C.c_float)]
     L.b200s_kernel_launches.restype = C.c_longlong
+    L.b200s_debug_set.restype = None
+    L.b200s_debug_set.argtypes = [C.c_int, C.c_int]
     if L.b200s_abi_version() != ABI_VERSION:
         raise LibraryMissing(f"{LIB_PATH} has ABI {L.b200s_abi_version()}, expected {ABI_VERSION}; rebuild it")
     _lib = L

@@ -69,6 +69,7 @@ int b200s_profile_read(float* ms) {
   g_nev = 0;
   return seen;
 }
+void b200s_debug_set(int which, int value) { if (which >= 0 && which < 4) b200s::g_sort_knobs[which] = value; }
 long long b200s_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 int b200s_last_cuda_error(void) { return g_last_cuda_error; }
 const char* b200s_build_info(void) {

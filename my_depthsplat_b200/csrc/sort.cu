@@ -28,23 +28,32 @@ __device__ __forceinline__ unsigned long long resolve_count(const CountRef& c) {
   return c.n_dev ? *c.n_dev : c.n_host;
 }
 
-// lanes of the warp holding the same 8-bit digit (all 32 lanes must call)
+// lanes of the warp holding the same 8-bit digit (all 32 lanes must call).
+// MODE 0: eight VOTE.BALLOTs + logic (ALU pipe); MODE 1: one MATCH.ANY (ADU pipe, ~20 slots each).
+// The two pipes are independent, so the ranking loop alternates them (tuning knob).
+template <int MODE>
 __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
-#if defined(B200S_MATCH_BALLOT)
-  uint32_t peers = 0xffffffffu;
+  if (MODE == 0) {
+    uint32_t peers = 0xffffffffu;
 #pragma unroll
-  for (int b = 0; b < 8; b++) {
-    const bool bit = (d >> b) & 1u;
-    const uint32_t m = __ballot_sync(0xffffffffu, bit);
-    peers &= bit ? m : ~m;
+    for (int b = 0; b < 8; b++) {
+      const bool bit = (d >> b) & 1u;
+      const uint32_t m = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? m : ~m;
+    }
+    return peers;
+  } else {
+    return __match_any_sync(0xffffffffu, d);
   }
-  return peers;
-#else
-  return __match_any_sync(0xffffffffu, d);
-#endif
 }
 
+// run-time tuning knobs (b200s_debug_set): [0] histogram variant, [1] ranking variant
+int g_sort_knobs[4] = {2, 2, 0, 0};
+
 // ---------------------------------------------------------------------------------------------
+// HMODE 0/1: warp-aggregated by digit match (ballots / MATCH.ANY), plain read-modify-write by the group
+// leader on a per-warp private histogram; HMODE 2: one shared-memory atomic per lane.
+template <int HMODE>
 __global__ void __launch_bounds__(SORT_THREADS) digit_histogram_kernel(const uint64_t* __restrict__ keys, CountRef cnt, uint32_t* __restrict__ hist,
                                                                        int passes) {
   extern __shared__ uint32_t s_hist[];  // [SORT_WARPS][passes][256]
@@ -65,8 +74,10 @@ __global__ void __launch_bounds__(SORT_THREADS) digit_histogram_kernel(const uin
       const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
       if (__all_sync(0xffffffffu, d == d0)) {
         if (lane == 0) my[p * RADIX + d0] += __popc(vmask);
+      } else if (HMODE == 2) {
+        if (valid) atomicAdd(&my[p * RADIX + d], 1u);
       } else {
-        const uint32_t peers = match_digit(d) & vmask;
+        const uint32_t peers = match_digit<HMODE>(d) & vmask;
         if (valid && lane == (__ffs(peers) - 1)) my[p * RADIX + d] += __popc(peers);
       }
       __syncwarp();
@@ -111,9 +122,30 @@ struct PassArgs {
   int shift;
 };
 
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const PassArgs a) {
-  __shared__ __align__(16) uint64_t s_keys[SORT_TILE];  // reused as u32 values
-  __shared__ uint32_t s_wc[SORT_WARPS][RADIX];
+// 16-byte async global->shared copy; bytes past src_bytes are zero-filled and not read
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+constexpr int LOOKBACK_BATCH = 8;
+// dynamic shared memory of the pass kernel
+constexpr size_t SWEEP_SMEM = SORT_TILE * 8 + SORT_TILE * 4 + SORT_TILE * 4 + SORT_WARPS * RADIX * 4;
+
+template <int RMODE>
+__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char sweep_smem[];
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(sweep_smem);                              // [4096] keys in sorted order
+  uint32_t* s_vin = reinterpret_cast<uint32_t*>(sweep_smem + SORT_TILE * 8);               // [4096] values as they arrive
+  uint32_t* s_vout = s_vin + SORT_TILE;                                                    // [4096] values in sorted order
+  uint32_t(*s_wc)[RADIX] = reinterpret_cast<uint32_t(*)[RADIX]>(s_vout + SORT_TILE);       // [8][256]
   __shared__ uint32_t s_goff[RADIX];
   __shared__ uint32_t s_dstart[RADIX];
   __shared__ uint32_t s_scan[SORT_WARPS];
@@ -123,13 +155,29 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const PassA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
 #pragma unroll
-  for (int w = 0; w < SORT_WARPS; w++) s_wc[w][tid] = 0;
+  for (int w = 0; w < SORT_WARPS; w++) { s_wc[w][tid] = 0; if (RMODE == 3) s_vout[w * RADIX + tid] = 0; }
   __syncthreads();
   const uint32_t tile = s_tile;
   const unsigned long long base = (unsigned long long)tile * SORT_TILE;
   if (base >= n) return;
   const uint32_t nvalid = (uint32_t)min((unsigned long long)SORT_TILE, n - base);
   a.lb_next[(size_t)tile * RADIX + tid] = 0;
+
+  // ---- the tile's values start travelling to shared memory now; they are needed only at the very end
+  {
+    const uint32_t* vsrc = a.vals_in + base;
+    if ((reinterpret_cast<uintptr_t>(vsrc) & 15) == 0) {
+#pragma unroll
+      for (int c = tid; c < SORT_TILE / 4; c += SORT_THREADS) {
+        const int rem = (int)nvalid - c * 4;
+        const int bytes = rem >= 4 ? 16 : (rem > 0 ? rem * 4 : 0);
+        cp_async_16(s_vin + c * 4, vsrc + (bytes ? c * 4 : 0), bytes);
+      }
+    } else {
+      for (int e = tid; e < SORT_TILE; e += SORT_THREADS) cp_async_4(s_vin + e, vsrc + (e < (int)nvalid ? e : 0), e < (int)nvalid ? 4 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
 
   // ---- load keys, warp-striped: item i of lane l of warp w is element w*512 + i*32 + l of the tile
   uint64_t key[SORT_ITEMS];
@@ -143,13 +191,21 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const PassA
   uint32_t rank[SORT_ITEMS];
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t* wc = s_wc[warp];
+  uint32_t* mm = s_vout + warp * RADIX;  // RMODE 3: per-warp match masks (s_vout is idle until the very end)
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const uint32_t d = (uint32_t)(key[i] >> a.shift) & 255u;
-    const uint32_t peers = match_digit(d);
+    uint32_t peers;
+    if (RMODE == 3) {  // lanes OR their bit into the digit's mask word: one shared atomic instead of eight votes
+      atomicOr(&mm[d], 1u << lane);
+      __syncwarp();
+      peers = mm[d];
+    } else {
+      peers = RMODE == 2 ? ((i & 1) ? match_digit<1>(d) : match_digit<0>(d)) : match_digit<(RMODE == 1 ? 1 : 0)>(d);
+    }
     const uint32_t r = wc[d];
     __syncwarp();
-    if (lane == (__ffs(peers) - 1)) wc[d] = r + __popc(peers);
+    if (lane == (__ffs(peers) - 1)) { wc[d] = r + __popc(peers); if (RMODE == 3) mm[d] = 0; }
     __syncwarp();
     rank[i] = r + __popc(peers & lt);
   }
@@ -165,14 +221,25 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const PassA
       st_volatile_u32(row, LB_FLAG_PREFIX | run);
     } else {
       st_volatile_u32(row, LB_FLAG_AGG | run);
+      // decoupled look-back, LOOKBACK_BATCH predecessors per round trip
       int t = (int)tile - 1;
-      while (true) {
-        const uint32_t w = ld_volatile_u32(a.lb_cur + (size_t)t * RADIX + tid);
-        const uint32_t f = w >> 30;
-        if (f == 0) continue;
-        prev += w & LB_VALUE_MASK;
-        if (f == 2) break;
-        t--;
+      bool found = false;
+      while (!found) {
+        uint32_t w[LOOKBACK_BATCH];
+#pragma unroll
+        for (int k = 0; k < LOOKBACK_BATCH; k++)
+          w[k] = (t - k >= 0) ? ld_volatile_u32(a.lb_cur + (size_t)(t - k) * RADIX + tid) : LB_FLAG_PREFIX;
+        int adv = 0;
+#pragma unroll
+        for (int k = 0; k < LOOKBACK_BATCH; k++) {
+          const uint32_t f = w[k] >> 30;
+          if (!found && adv == k && f != 0) {
+            prev += w[k] & LB_VALUE_MASK;
+            adv = k + 1;
+            if (f == 2) found = true;
+          }
+        }
+        t -= adv;
       }
       st_volatile_u32(row, LB_FLAG_PREFIX | (prev + run));
     }
@@ -190,36 +257,31 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const PassA
   s_dstart[tid] = dstart;
   s_goff[tid] = a.gbase[tid] + prev - dstart;
   __syncthreads();
-  // ---- reorder keys through shared memory
-  uint32_t pos[SORT_ITEMS];
+  // ---- reorder keys through shared memory (rank[] becomes the in-tile sorted position)
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const uint32_t d = (uint32_t)(key[i] >> a.shift) & 255u;
-    pos[i] = s_dstart[d] + wc[d] + rank[i];
-    s_keys[pos[i]] = key[i];
+    rank[i] += s_dstart[d] + wc[d];
+    s_keys[rank[i]] = key[i];
   }
+  // values have landed by now; wait for this thread's copies, the barrier below makes all of them visible
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  uint32_t gpos[SORT_ITEMS];
-#pragma unroll
-  for (int j = 0; j < SORT_ITEMS; j++) {
-    const uint32_t e = j * SORT_THREADS + tid;
-    const uint64_t k = s_keys[e];
-    gpos[j] = s_goff[(uint32_t)(k >> a.shift) & 255u] + e;
-    if (e < nvalid) a.keys_out[gpos[j]] = k;
-  }
-  __syncthreads();
-  // ---- values take the same route
-  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys);
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const uint32_t e = wbase + i * 32;
-    if (e < nvalid) s_vals[pos[i]] = __ldg(a.vals_in + base + e);
+    if (e < nvalid) s_vout[rank[i]] = s_vin[e];
+  }
+#pragma unroll
+  for (int j = 0; j < SORT_ITEMS; j++) {
+    const uint32_t e = j * SORT_THREADS + tid;
+    if (e < nvalid) { const uint64_t k = s_keys[e]; a.keys_out[s_goff[(uint32_t)(k >> a.shift) & 255u] + e] = k; }
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < SORT_ITEMS; j++) {
     const uint32_t e = j * SORT_THREADS + tid;
-    if (e < nvalid) a.vals_out[gpos[j]] = s_vals[e];
+    if (e < nvalid) { const uint64_t k = s_keys[e]; a.vals_out[s_goff[(uint32_t)(k >> a.shift) & 255u] + e] = s_vout[e]; }
   }
 }
 
@@ -263,7 +325,9 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     const size_t smem = (size_t)SORT_WARPS * passes * RADIX * sizeof(uint32_t);
     static thread_local size_t configured = 0;
     if (smem > configured) {
-      if ((e = cudaFuncSetAttribute(digit_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(digit_histogram_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(digit_histogram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(digit_histogram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
       configured = smem;
     }
     long long blocks = (n_cap + SORT_THREADS * 16 - 1) / (SORT_THREADS * 16);
@@ -271,11 +335,23 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     stage_mark(B200S_STAGE_SORT_HIST, stream);
-    digit_histogram_kernel<<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+    if (g_sort_knobs[0] == 0) digit_histogram_kernel<0><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+    else if (g_sort_knobs[0] == 1) digit_histogram_kernel<1><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+    else digit_histogram_kernel<2><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
     digit_scan_kernel<<<1, RADIX, 0, stream>>>(hist, passes);
     count_launches(2);
   }
   stage_mark(B200S_STAGE_SORT_PASSES, stream);
+  {
+    static thread_local bool sweep_configured = false;
+    if (!sweep_configured) {
+      if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
+      sweep_configured = true;
+    }
+  }
   for (int p = 0; p < passes; p++) {
     PassArgs a;
     a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout;
@@ -284,7 +360,11 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     a.lb_next = lookback + (size_t)((p + 1) & 1) * tiles * RADIX;
     a.tile_counter = counters + CNT_SORT_TILE0 + p;
     a.cnt = cnt; a.shift = 8 * p;
-    onesweep_pass_kernel<<<tiles - 1 > 0 ? tiles - 1 : 1, SORT_THREADS, 0, stream>>>(a);
+    const int nblk = tiles - 1 > 0 ? tiles - 1 : 1;
+    if (g_sort_knobs[1] == 0) onesweep_pass_kernel<0><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
+    else if (g_sort_knobs[1] == 1) onesweep_pass_kernel<1><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
+    else if (g_sort_knobs[1] == 2) onesweep_pass_kernel<2><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
+    else onesweep_pass_kernel<3><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
     count_launches(1);
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
