@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 1
+#define B200S_ABI_VERSION 2
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -130,6 +130,9 @@ typedef struct B200sOut {
   float* depth;      /* [VV,H,W] or NULL (required when depth_mode != NONE) */
   int32_t* radii;    /* [VV,N] or NULL */
   int32_t count_work;/* != 0: accumulate tested/blended/max_tile_len into the status block */
+  void* status_host; /* optional: DEVICE-ACCESSIBLE pointer to 16 bytes of mapped pinned host memory (b200s_host_alloc).
+                        Stage A stores {u64 num_pairs, u32 overflow, u32 1} there directly from the kernel, so the
+                        host can read the pair count after an event wait without occupying a copy engine. */
 } B200sOut;
 
 typedef struct B200sGradOut { /* upstream gradients */
@@ -192,6 +195,11 @@ long long b200s_kernel_launches(void);
 /* Tuning knobs for A/B measurements (not part of the stable contract): which 0 = digit-histogram variant
  * (0 ballots, 1 MATCH.ANY, 2 shared atomics), which 1 = ranking variant (0 ballots, 1 MATCH.ANY, 2 alternating). */
 void b200s_debug_set(int which, int value);
+
+/* Host-memory utility (not on the data path): mapped, portable pinned memory that kernels can write
+ * (cudaHostAlloc).  Under unified addressing the returned pointer is valid on host and device. */
+void* b200s_host_alloc(size_t bytes);
+void b200s_host_free(void* p);
 
 int b200s_abi_version(void);
 int b200s_last_cuda_error(void);       /* cudaError_t of the last failed launch on this thread */

@@ -10,7 +10,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200splat.so"
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 B200S_OK, B200S_EBADARG, B200S_ECUDA = 0, 1, 3
 COV_3X3, COV_UPPER6 = 0, 1
@@ -64,7 +64,7 @@ class Status(C.Structure):
 
 
 class Out(C.Structure):
-    _fields_ = [("color", _f32p), ("depth", _f32p), ("radii", C.c_void_p), ("count_work", C.c_int32)]
+    _fields_ = [("color", _f32p), ("depth", _f32p), ("radii", C.c_void_p), ("count_work", C.c_int32), ("status_host", C.c_void_p)]
 
 
 class GradOut(C.Structure):
@@ -82,7 +82,7 @@ class GradIn(C.Structure):
 EXPORTS = (
     "b200s_plan", "b200s_forward_bin", "b200s_forward_render", "b200s_backward", "b200s_sort_tmp_bytes",
     "b200s_sort_pairs", "b200s_abi_version", "b200s_last_cuda_error", "b200s_build_info", "b200s_profile_enable",
-    "b200s_profile_read", "b200s_kernel_launches", "b200s_debug_set",
+    "b200s_profile_read", "b200s_kernel_launches", "b200s_debug_set", "b200s_host_alloc", "b200s_host_free",
 )
 STAGES = ("pre_bin", "sort_hist", "sort_passes", "ranges", "comp_fwd", "grad_zero", "comp_bwd", "pre_bwd", "end")
 
@@ -128,6 +128,10 @@ def load() -> C.CDLL:
     L.b200s_profile_read.restype = C.c_int
     L.b200s_profile_read.argtypes = [P(C.c_float)]
     L.b200s_kernel_launches.restype = C.c_longlong
+    L.b200s_host_alloc.restype = C.c_void_p
+    L.b200s_host_alloc.argtypes = [C.c_size_t]
+    L.b200s_host_free.restype = None
+    L.b200s_host_free.argtypes = [C.c_void_p]
     L.b200s_debug_set.restype = None
     L.b200s_debug_set.argtypes = [C.c_int, C.c_int]
     if L.b200s_abi_version() != ABI_VERSION:

@@ -69,6 +69,13 @@ int b200s_profile_read(float* ms) {
   g_nev = 0;
   return seen;
 }
+void* b200s_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  memset(p, 0, bytes);
+  return p;
+}
+void b200s_host_free(void* p) { if (p) cudaFreeHost(p); }
 void b200s_debug_set(int which, int value) { if (which >= 0 && which < 4) b200s::g_sort_knobs[which] = value; }
 long long b200s_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 int b200s_last_cuda_error(void) { return g_last_cuda_error; }

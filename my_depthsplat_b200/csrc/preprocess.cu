@@ -30,6 +30,7 @@ struct PreArgs {
   uint32_t* counters;
   B200sStatus* status;
   int32_t* radii;
+  unsigned long long* status_host;  // mapped pinned host memory or NULL
 };
 
 constexpr uint64_t SCAN_FLAG_AGG = 1ull << 62, SCAN_FLAG_PREFIX = 2ull << 62, SCAN_VALUE_MASK = (1ull << 62) - 1;
@@ -238,6 +239,11 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_bin_kernel(const B200s
         const unsigned long long total = excl + block_total;
         a.status->num_pairs = total;
         a.status->overflow = total > a.pair_capacity ? 1u : 0u;
+        if (a.status_host) {  // straight to the host over PCIe: no copy engine, no extra launch
+          a.status_host[0] = total;
+          a.status_host[1] = (total > a.pair_capacity ? 1ull : 0ull) | (1ull << 32);
+          __threadfence_system();
+        }
       }
     }
   }
@@ -302,6 +308,7 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   a.counters = reinterpret_cast<uint32_t*>(scratch + plan.off_counters);
   a.status = reinterpret_cast<B200sStatus*>(saved + plan.off_status);
   a.radii = out ? out->radii : nullptr;
+  a.status_host = out ? reinterpret_cast<unsigned long long*>(out->status_host) : nullptr;
 
   cudaError_t e;
   stage_mark(B200S_STAGE_PRE_BIN, stream);

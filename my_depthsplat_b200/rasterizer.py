@@ -59,6 +59,29 @@ debug_keep = False
 debug_last: Optional[dict] = None
 
 
+class _HostStatusRing:
+    """64 slots of 16 bytes of mapped pinned host memory that stage A writes the pair count into."""
+    SLOTS = 64
+
+    def __init__(self):
+        L = _lib.load()
+        self.base = L.b200s_host_alloc(self.SLOTS * 16)
+        if not self.base:
+            raise RuntimeError("b200s_host_alloc failed")
+        self.words = (C.c_uint64 * (self.SLOTS * 2)).from_address(self.base)
+        self.next = 0
+
+    def take(self):
+        i = self.next
+        self.next = (i + 1) % self.SLOTS
+        self.words[2 * i] = 0
+        self.words[2 * i + 1] = 0
+        return i, self.base + 16 * i
+
+
+_status_ring: Optional[_HostStatusRing] = None
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -126,12 +149,16 @@ class _Rasterize(torch.autograd.Function):
         color = torch.empty((VV, 3, H, W), dtype=torch.float32, device=dev)
         depth = torch.empty((VV, H, W), dtype=torch.float32, device=dev) if vp.depth_mode is not None else None
         radii = torch.empty((VV, N), dtype=torch.int32, device=dev) if want_radii else None
-        out = _lib.Out(_ptr(color), _ptr(depth), _ptr(radii), 1 if count_work else 0)
+        global _status_ring
+        if _status_ring is None:
+            _status_ring = _HostStatusRing()
+        slot, slot_ptr = _status_ring.take()
+        out = _lib.Out(_ptr(color), _ptr(depth), _ptr(radii), 1 if count_work else 0, slot_ptr)
 
         key = (dev.index, B, N, VV, H, W)
         cap = _capacity_hint.get(key) or max(4 * N * VV, 1 << 16)
         cap = min(cap, (1 << 30) - 1)
-        host = torch.empty(8, dtype=torch.int64, pin_memory=True)
+        words = _status_ring.words
         retries = 0
         while True:
             plan = _lib.plan(B, N, VV, H, W, cap)
@@ -139,17 +166,22 @@ class _Rasterize(torch.autograd.Function):
             scratch = _scratch(dev, plan.scratch_bytes)
             _lib.check(L.b200s_forward_bin(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(),
                                            C.byref(out), stream), "b200s_forward_bin")
-            # the pair count travels to the host while the GPU already sorts and composites
-            host.copy_(saved[:64].view(torch.int64), non_blocking=True)
+            # stage A wrote the pair count straight into mapped host memory; the event marks its end, and the
+            # GPU already sorts and composites (speculatively, at this capacity) while the host looks at it
             ev = torch.cuda.Event()
             ev.record()
             _lib.check(L.b200s_forward_render(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(),
                                               C.byref(out), stream), "b200s_forward_render")
             ev.synchronize()
-            num_pairs = int(host[0].item())
-            overflow = int(host[1].item()) & 0xFFFFFFFF
+            num_pairs = int(words[2 * slot])
+            flags = int(words[2 * slot + 1])
+            if not (flags >> 32):
+                raise RuntimeError("stage A did not report its pair count (status word not written)")
+            overflow = flags & 0xFFFFFFFF
             if not overflow:
                 break
+            words[2 * slot] = 0
+            words[2 * slot + 1] = 0
             if num_pairs >= (1 << 30) - 1:
                 raise RuntimeError(f"{num_pairs} (tile, Gaussian) pairs in one call exceed the 2^30 limit; render fewer views per call")
             cap = min(int(num_pairs * 1.25) + 4096, (1 << 30) - 1)
@@ -157,11 +189,11 @@ class _Rasterize(torch.autograd.Function):
         _capacity_hint[key] = min(max(int(num_pairs * 1.25) + 4096, 1 << 16), (1 << 30) - 1)
 
         st = last_stats
-        st.num_pairs, st.num_visible = num_pairs, (int(host[1].item()) >> 32) & 0xFFFFFFFF
-        st.pair_capacity, st.retries = cap, retries
+        st.num_pairs, st.pair_capacity, st.retries = num_pairs, cap, retries
         if count_work:
             torch.cuda.current_stream(dev).synchronize()
             h = saved[:64].view(torch.int64).cpu()
+            st.num_visible = (int(h[1]) >> 32) & 0xFFFFFFFF
             st.tested, st.blended, st.max_tile_len = int(h[2]), int(h[3]), int(h[4]) & 0xFFFFFFFF
 
         if debug_keep:
