@@ -44,50 +44,62 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons.  ONE nvidia-smi process for the whole run, started before the
+    scene is built (its start-up takes seconds on a fresh box and would otherwise perturb, or miss, the
+    timed region); rows carry timestamps and each timed region keeps the rows that fall inside it."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index = index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
-
-    def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 7]
-        os.unlink(self.f.name)
-        sm, reasons = [], set()
-        for r in rows:
+    def _rows(self):
+        from datetime import datetime
+        out = []
+        for line in Path(self.f.name).read_text().strip().splitlines():
+            r = [x.strip() for x in line.split(",")]
+            if len(r) < 8:
+                continue
             try:
-                sm.append(float(r[1])); out["sm_max_mhz"] = float(r[2])
+                ts = datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                out.append((ts, float(r[1]), float(r[2]), r[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+        return out
+
+    def window(self, t0: float, t1: float) -> dict:
+        """Median SM clock and throttle reasons seen between wall-clock t0 and t1 (+- one sample period)."""
+        self.f.flush()
+        rows = self._rows()
+        sel = [r for r in rows if t0 - 0.25 <= r[0] <= t1 + 0.25] or rows[-3:]
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(sel)}
+        reasons = set()
+        sm = sorted(r[1] for r in sel)
+        if sm:
+            out["sm_mhz"], out["sm_max_mhz"] = sm[len(sm) // 2], sel[0][2]
+        for r in sel:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if "Active" in v and "Not" not in v:
                     reasons.add(name)
-        if sm:
-            sm.sort()
-            out["sm_mhz"] = sm[len(sm) // 2]
         out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
         return out
+
+    def close(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -162,6 +174,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -233,7 +246,8 @@ def run_ours(args):
         e2e_state["pending"] = i + 1
         color, grads = step(dev_in[slot])
         ev_free[slot].record(cur)
-        outs = [color] + (list(grads) if isinstance(grads, (tuple, list)) else [grads])
+        # detach: copy_() from a tensor with history would chain every step's autograd graph onto host_out
+        outs = [color.detach()] + [g.detach() for g in (grads if isinstance(grads, (tuple, list)) else [grads])]
         ev_done.record(cur)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done)
@@ -250,6 +264,10 @@ def run_ours(args):
             inflight[0][0].synchronize()
             inflight.pop(0)
         e2e_state["i"] = i + 1
+        if os.environ.get("B200S_E2E_TRACE"):
+            st_ = torch.cuda.memory_stats(dev)
+            print(f"e2e step {i}: reserved {st_['reserved_bytes.all.current'] / 2**30:.2f} GiB, allocated {st_['allocated_bytes.all.current'] / 2**30:.2f} GiB, "
+                  f"device_allocs {st_['num_device_alloc']}, inflight {len(inflight)}", file=sys.stderr, flush=True)
         return outs
 
     def timed(fn, steps, warmup, finish=None):
@@ -258,10 +276,9 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = L.b200s_kernel_launches()
+        wall0 = time.time()
         e0.record()
         for _ in range(steps):
             fn()
@@ -271,7 +288,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         launches = L.b200s_kernel_launches() - l0
-        clocks = sampler.stop()
+        clocks = sampler.window(wall0, time.time())
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,7 +307,10 @@ def run_ours(args):
         cur.wait_stream(s_out)
         cur.wait_stream(s_in)
 
-    ms_e, _, _ = timed(step_e2e, args.steps, 2, finish=e2e_finish)
+    ms0 = torch.cuda.memory_stats(dev)
+    ms_e, _, _ = timed(step_e2e, args.steps, W_ + 3, finish=e2e_finish)  # extra warm-up: the caching allocator must reach its steady state
+    ms1 = torch.cuda.memory_stats(dev)
+    alloc_events = {k: ms1.get(k, 0) - ms0.get(k, 0) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")}
 
     # raw pinned-memory copy bandwidth of this box, to read the e2e number against
     def copy_gbs(dst, src):
@@ -379,7 +399,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (Gaussians 472 MB + 64 B records per view)" if N * 160 > 126e6 else "inputs fit L2",
                        "parallelism": f"view-sharded x{world}, Gaussians replicated" + (", NCCL all-reduce of per-Gaussian grads" if world > 1 else "")},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(ms_step_e, 4), "pinned_copy_bandwidth": pcie,
+                    "ms_per_step": round(ms_step_e, 4), "pinned_copy_bandwidth": pcie, "allocator_events": alloc_events,
                     "note": "3-stream pipeline: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i"},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -391,6 +411,7 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
+    sampler.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -25,7 +25,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from .projection import get_fov, homogenize_points
+from .projection import get_fov, homogenize_points, inverse_nosync
 from .rasterizer import ViewPack, rasterize
 
 DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
@@ -54,7 +54,7 @@ def _camera_block(extrinsics: Tensor, near: Tensor, far: Tensor, fov_x: Tensor, 
     """View / full-projection matrices in the transposed storage the rasterizer consumes, camera
     positions and tanfov -- the reference's lines :83-86 and :101-110, batched."""
     projection = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
-    view = extrinsics.inverse().transpose(1, 2)
+    view = inverse_nosync(extrinsics).transpose(1, 2)
     full = view @ projection
     campos = extrinsics[:, :3, 3]
     tanfov = torch.stack([tan_fov_x.expand(near.shape[0]), tan_fov_y.expand(near.shape[0])], dim=-1)
@@ -63,7 +63,7 @@ def _camera_block(extrinsics: Tensor, near: Tensor, far: Tensor, fov_x: Tensor, 
 
 def _depth_block(extrinsics_raw: Tensor, near_raw: Tensor, far_raw: Tensor):
     """Row 2 of the UNnormalised world->camera matrix: z_cam = row . (mean, 1) (reference :238-241)."""
-    w2c = extrinsics_raw.inverse()
+    w2c = inverse_nosync(extrinsics_raw)
     return w2c[:, 2, :].contiguous(), torch.stack([near_raw, far_raw], dim=-1).contiguous()
 
 

@@ -18,6 +18,13 @@ def homogenize_points(points: Tensor) -> Tensor:
     return torch.cat([points, one], dim=-1)
 
 
+def inverse_nosync(m: Tensor) -> Tensor:
+    """``m.inverse()`` without its device->host synchronisation: ``Tensor.inverse`` reads back LAPACK's
+    ``info`` to raise on singular input, which stalls the host until the GPU has drained.  ``inv_ex`` runs
+    the same factorisation (bit-identical result) and leaves ``info`` on the device."""
+    return torch.linalg.inv_ex(m, check_errors=False).inverse
+
+
 def _unit_ray(k_inv: Tensor, u: float, v: float) -> Tensor:
     pixel = torch.tensor([u, v, 1.0], dtype=torch.float32, device=k_inv.device)
     ray = torch.einsum("bij,j->bi", k_inv, pixel)
@@ -28,7 +35,7 @@ def get_fov(intrinsics: Tensor) -> Tensor:
     """Normalised intrinsics [b,3,3] -> [b,2] = (fov_x, fov_y): the angle between the unprojected
     rays through opposite edge mid-points.  The principal point does not survive this (the
     frustum built from it is symmetric), exactly as in the reference."""
-    k_inv = intrinsics.inverse()
+    k_inv = inverse_nosync(intrinsics)
     left, right, top, bottom = (_unit_ray(k_inv, u, v) for u, v in _EDGE_MIDPOINTS)
     fov_x = (left * right).sum(dim=-1).acos()
     fov_y = (top * bottom).sum(dim=-1).acos()

@@ -105,8 +105,40 @@ def _scratch(device, nbytes: int) -> torch.Tensor:
     return buf
 
 
+class _SavedLease:
+    """A forward->backward workspace taken from a small per-(device, stream) pool.  The caching allocator
+    handles these ~1 GB blocks badly when the caller keeps results of earlier steps alive (fresh
+    cudaMalloc / cudaFree every few steps, 10-200 ms each on a B200 box), so they are recycled here: the
+    lease returns its buffer to the pool when the autograd context that holds it dies."""
+    __slots__ = ("tensor", "key")
+
+    def __init__(self, device, nbytes: int):
+        self.key = (device, torch.cuda.current_stream(device).cuda_stream)
+        pool = _saved_pool.setdefault(self.key, [])
+        best = None
+        for i, t in enumerate(pool):
+            if t.numel() >= nbytes and (best is None or t.numel() < pool[best].numel()):
+                best = i
+        if best is not None and pool[best].numel() <= 2 * nbytes + (1 << 20):
+            self.tensor = pool.pop(best)
+        else:
+            self.tensor = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
+
+    def __del__(self):
+        try:
+            pool = _saved_pool.setdefault(self.key, [])
+            if len(pool) < 4:
+                pool.append(self.tensor)
+        except Exception:
+            pass
+
+
+_saved_pool: dict = {}
+
+
 def release_scratch() -> None:
     _scratch_cache.clear()
+    _saved_pool.clear()
 
 
 class _Ctx:
@@ -160,10 +192,14 @@ class _Rasterize(torch.autograd.Function):
         cap = min(cap, (1 << 30) - 1)
         words = _status_ring.words
         retries = 0
+        import time as _t
+        _t0 = _t.perf_counter()
         while True:
             plan = _lib.plan(B, N, VV, H, W, cap)
-            saved = torch.empty(plan.saved_bytes, dtype=torch.uint8, device=dev)
+            lease = _SavedLease(dev, plan.saved_bytes)
+            saved = lease.tensor
             scratch = _scratch(dev, plan.scratch_bytes)
+            _t1 = _t.perf_counter()
             _lib.check(L.b200s_forward_bin(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(),
                                            C.byref(out), stream), "b200s_forward_bin")
             # stage A wrote the pair count straight into mapped host memory; the event marks its end, and the
@@ -172,7 +208,11 @@ class _Rasterize(torch.autograd.Function):
             ev.record()
             _lib.check(L.b200s_forward_render(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(),
                                               C.byref(out), stream), "b200s_forward_render")
+            _t2 = _t.perf_counter()
             ev.synchronize()
+            _t3 = _t.perf_counter()
+            if debug_keep == "timing":
+                print(f"    fwd host: alloc {1e3*(_t1-_t0):.2f} enqueue {1e3*(_t2-_t1):.2f} wait {1e3*(_t3-_t2):.2f} ms", flush=True)
             num_pairs = int(words[2 * slot])
             flags = int(words[2 * slot + 1])
             if not (flags >> 32):
@@ -200,7 +240,7 @@ class _Rasterize(torch.autograd.Function):
             global debug_last
             debug_last = dict(plan=plan, saved=saved, scratch=scratch, num_pairs=num_pairs, N=N, VV=VV, H=H, W=W)
         ctx.save_for_backward(means, covs, colors, opacities)
-        ctx.b200 = (vp, use_sh, sh_degree, sh_layout, plan, saved, means2d is not None)
+        ctx.b200 = (vp, use_sh, sh_degree, sh_layout, plan, lease, means2d is not None)
         outs = [color]
         if depth is not None:
             outs.append(depth)
@@ -216,7 +256,8 @@ class _Rasterize(torch.autograd.Function):
     def backward(ctx, g_color, g_depth, _g_radii):
         L = _lib.load()
         means, covs, colors, opacities = ctx.saved_tensors
-        vp, use_sh, sh_degree, sh_layout, plan, saved, want_m2d = ctx.b200
+        vp, use_sh, sh_degree, sh_layout, plan, lease, want_m2d = ctx.b200
+        saved = lease.tensor
         dev = means.device
         VV, N = vp.scene_index.shape[0], means.shape[1]
         stream = torch.cuda.current_stream(dev).cuda_stream
