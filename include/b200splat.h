@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 2
+#define B200S_ABI_VERSION 3
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -107,7 +107,10 @@ typedef struct B200sPlan {
   size_t scratch_bytes;
   size_t off_keys_a, off_keys_b; /* [R_cap] u64 each */
   size_t off_vals_b;             /* [R_cap] u32 */
-  size_t off_scan_state;         /* [pre_tickets] u64 decoupled look-back words */
+  size_t off_scan_state;         /* [pre_tickets] u64 exclusive pair offset of every projection CTA */
+  size_t off_ticket_totals;      /* [pre_tickets] u32 tile total of every projection CTA */
+  size_t off_scan_blocks;        /* [pre_tickets / 2048 + 1] u64 decoupled look-back words of the scan */
+  size_t off_bin_info;           /* [pre_tickets * 256] uint2 (depth bits, packed rect) per Gaussian-view */
   size_t off_hist;               /* [8,256] u32 digit histograms -> exclusive bases */
   size_t off_lookback;           /* [2, sort_tiles_cap, 256] u32 onesweep look-back words */
   size_t off_counters;           /* [64] u32 ticket / tile counters */

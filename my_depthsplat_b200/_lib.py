@@ -10,7 +10,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200splat.so"
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 B200S_OK, B200S_EBADARG, B200S_ECUDA = 0, 1, 3
 COV_3X3, COV_UPPER6 = 0, 1
@@ -51,7 +51,8 @@ class Plan(C.Structure):
         ("saved_bytes", C.c_size_t), ("off_status", C.c_size_t), ("off_rec", C.c_size_t), ("off_vals_a", C.c_size_t),
         ("off_ranges", C.c_size_t), ("off_final_T", C.c_size_t), ("off_n_contrib", C.c_size_t),
         ("scratch_bytes", C.c_size_t), ("off_keys_a", C.c_size_t), ("off_keys_b", C.c_size_t), ("off_vals_b", C.c_size_t),
-        ("off_scan_state", C.c_size_t), ("off_hist", C.c_size_t), ("off_lookback", C.c_size_t), ("off_counters", C.c_size_t),
+        ("off_scan_state", C.c_size_t), ("off_ticket_totals", C.c_size_t), ("off_scan_blocks", C.c_size_t),
+        ("off_bin_info", C.c_size_t), ("off_hist", C.c_size_t), ("off_lookback", C.c_size_t), ("off_counters", C.c_size_t),
         ("off_grad_rec", C.c_size_t),
     ]
 

@@ -125,6 +125,9 @@ int b200s_plan(const B200sDims* d, B200sPlan* p) {
   p->off_keys_b = o; o = align_up(o + R * 8);
   p->off_vals_b = o; o = align_up(o + R * 4);
   p->off_scan_state = o; o = align_up(o + (size_t)p->pre_tickets * 8);
+  p->off_ticket_totals = o; o = align_up(o + (size_t)p->pre_tickets * 4);
+  p->off_scan_blocks = o; o = align_up(o + ((size_t)p->pre_tickets / 2048 + 2) * 8);
+  p->off_bin_info = o; o = align_up(o + (size_t)p->pre_tickets * PRE_THREADS * 8);
   p->off_hist = o; o = align_up(o + 8 * 256 * 4);
   p->off_lookback = o; o = align_up(o + 2 * (size_t)p->sort_tiles_cap * 256 * 4);
   p->off_counters = o; o = align_up(o + CNT_WORDS * 4);

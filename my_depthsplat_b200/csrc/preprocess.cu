@@ -1,17 +1,26 @@
-// preprocess.cu -- stage A of forward: ONE kernel that replaces the extension's preprocessCUDA,
-// cub::DeviceScan::InclusiveSum (+ its blocking D2H read) and duplicateWithKeys:
+// preprocess.cu -- stage A of forward.  Replaces the extension's preprocessCUDA,
+// cub::DeviceScan::InclusiveSum (+ its blocking D2H read of the total) and duplicateWithKeys
+//  with three kernels and no host synchronisation:
 //
-//   ticket (dynamic block id, view-fastest so that the blocks that read the same 256 Gaussians for
-//   different views run together and share them through L2)
-//     -> coalesced float4 staging of the Gaussian chunk (means, covariances, SH, opacities) into
-//        shared memory in the caller's own tensor layouts (no transposition copies)
-//     -> per thread: cull, projection, EWA cov2D, conic, radius, tile rect, SH->RGB, depth colour
-//     -> 64-byte projected records written back coalesced through shared memory
-//     -> block scan of tiles_touched + single-pass decoupled look-back across tickets
-//     -> emission of 64-bit (view | tile | depth-bits) keys and Gaussian-index values at the scanned
-//        offsets: per thread for small rects, one warp per large-rect Gaussian otherwise.
+//   project_kernel   one CTA per (256-Gaussian chunk, view), view-fastest so that the CTAs that read
+//                    the same chunk for different views run together and share it through L2:
+//                    coalesced float4 staging of means / covariances / SH / opacities in the caller's
+//                    own tensor layouts -> cull, projection, EWA cov2D, conic, radius, tile rect,
+//                    SH->RGB, depth colour -> 64-byte records out (coalesced through shared memory),
+//                    8-byte (depth bits, packed rect) binning word per Gaussian, tile total per CTA.
+//   scan_kernel      single-pass chained scan (decoupled look-back) of the per-CTA tile totals; writes
+//                    the pair count and the overflow flag to the device status block AND straight into
+//                    mapped pinned host memory.
+//   emit_kernel      64-bit (view | tile | depth-bits) keys and Gaussian-index values at the scanned
+//                    offsets: per thread for small rects, one warp per large-rect Gaussian otherwise.
 //
-// HBM-bound: per (view, Gaussian) 148 B read (L2-shared across views) + 64 B record + 12 B per pair.
+// (An earlier version chained the scan through the projection CTAs themselves; with ~46k CTAs in flight
+// order the look-back latency, not HBM, bounded the kernel -- 28 % of warp samples sat at the barrier
+// behind the look-back, profiles/r1b.  Scanning 46k totals separately costs one 8-byte word per
+// Gaussian-view of extra traffic and removes the wait.)
+//
+// HBM-bound: per (view, Gaussian) 148 B read (L2-shared across views) + 72 B written, + 8 B read and
+// 12 B per pair written by the emission.
 #include "kernels.cuh"
 
 namespace b200s {
@@ -26,7 +35,10 @@ struct PreArgs {
   Rec* rec;
   uint64_t* keys;
   uint32_t* vals;
-  uint64_t* scan_state;
+  uint2* bin_info;                  // [VV*chunks*256] (depth bits, packed rect) in ticket order
+  uint32_t* ticket_totals;          // [n_tickets]
+  unsigned long long* ticket_offsets;  // [n_tickets] exclusive scan of the totals
+  uint64_t* scan_blocks;            // [scan blocks] decoupled look-back words
   uint32_t* counters;
   B200sStatus* status;
   int32_t* radii;
@@ -74,18 +86,13 @@ __device__ __forceinline__ float eval_sh_channel(int deg, const float* sh, int k
   return r;
 }
 
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_bin_kernel(const B200sScene sc, const B200sViews vw, const PreArgs a) {
+__global__ void __launch_bounds__(PRE_THREADS) project_kernel(const B200sScene sc, const B200sViews vw, const PreArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ ViewParams vp;
-  __shared__ int s_ticket;
   __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
-  __shared__ unsigned long long s_base;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_ticket = (int)atomicAdd(&a.counters[CNT_PRE_TICKET], 1u);
-  __syncthreads();
-  const int ticket = s_ticket;
-  if (ticket >= a.n_tickets) return;
+  const int ticket = blockIdx.x;  // view-fastest: ticket = chunk * VV + view
   const int view = ticket % a.VV, chunk = ticket / a.VV;
   if (tid == 0) load_view_params(vp, vw, view, a.H, a.W);
   __syncthreads();
@@ -191,52 +198,76 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_bin_kernel(const B200s
     if (a.radii) a.radii[(long long)view * a.N + i0 + tid] = tiles > 0 ? __float_as_int(out.q3.y) : 0;
   }
 
-  // ---- records out, coalesced through shared memory -------------------------------------------
-  __syncthreads();  // everyone is done reading the staged inputs
+  // ---- binning word, tile total of the CTA, records out ----------------------------------------------
   {
-    float4* s_rec = reinterpret_cast<float4*>(smem);  // [256*4]
-    s_rec[tid * 4 + 0] = out.q0; s_rec[tid * 4 + 1] = out.q1; s_rec[tid * 4 + 2] = out.q2; s_rec[tid * 4 + 3] = out.q3;
-    __syncthreads();
-    float4* dst = reinterpret_cast<float4*>(a.rec + (long long)view * a.N + i0);
-    for (int i = tid; i < n * 4; i += PRE_THREADS) dst[i] = s_rec[i];
+    const uint32_t rect = tiles ? ((uint32_t)rx0 | ((uint32_t)ry0 << 8) | ((uint32_t)rx1 << 16) | ((uint32_t)ry1 << 24)) : 0u;
+    a.bin_info[(size_t)ticket * PRE_THREADS + tid] = make_uint2(__float_as_uint(depth), rect);
   }
-
-  // ---- block scan of tiles_touched -----------------------------------------------------------
-  uint32_t incl = tiles;
+  uint32_t sum = tiles;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-  if (lane == 31) s_warp_tot[warp] = incl;
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (lane == 0) s_warp_tot[warp] = sum;
   const uint32_t vis_mask = __ballot_sync(0xffffffffu, tiles > 0);
-  __syncthreads();
-  uint32_t warp_excl = 0, block_total = 0;
-#pragma unroll
-  for (int w = 0; w < PRE_THREADS / 32; w++) { const uint32_t t = s_warp_tot[w]; if (w < warp) warp_excl += t; block_total += t; }
-  const uint32_t my_excl = warp_excl + incl - tiles;
   if (lane == 0 && vis_mask) atomicAdd(&a.status->num_visible, (uint32_t)__popc(vis_mask));
-
-  // ---- decoupled look-back over tickets (warp 0) ------------------------------------------------
-  if (warp == 0) {
-    if (lane == 0) st_volatile_u64(&a.scan_state[ticket], (ticket == 0 ? SCAN_FLAG_PREFIX : SCAN_FLAG_AGG) | (uint64_t)block_total);
-    unsigned long long excl = 0;
-    int idx = ticket - 1;  // window covers [idx-31, idx]
-    while (idx >= 0) {
-      const int t = idx - lane;
-      uint64_t w = SCAN_FLAG_PREFIX;  // tickets < 0 count as an empty prefix
-      if (t >= 0) { do { w = ld_volatile_u64(&a.scan_state[t]); } while ((w >> 62) == 0); }
-      const uint32_t pmask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-      const int first = pmask ? (__ffs(pmask) - 1) : 32;
-      unsigned long long v = (lane <= first) ? (w & SCAN_VALUE_MASK) : 0ull;
+  __syncthreads();  // everyone is done reading the staged inputs; warp totals visible
+  if (tid == 0) {
+    uint32_t t = 0;
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-      excl += v;
+    for (int w = 0; w < PRE_THREADS / 32; w++) t += s_warp_tot[w];
+    a.ticket_totals[ticket] = t;
+  }
+  float4* s_rec = reinterpret_cast<float4*>(smem);  // [256*4]
+  s_rec[tid * 4 + 0] = out.q0; s_rec[tid * 4 + 1] = out.q1; s_rec[tid * 4 + 2] = out.q2; s_rec[tid * 4 + 3] = out.q3;
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(a.rec + (long long)view * a.N + i0);
+  for (int i = tid; i < n * 4; i += PRE_THREADS) dst[i] = s_rec[i];
+}
+
+// -------------------------------------------------------------------------------------------------
+// Single-pass chained scan of the per-ticket totals (decoupled look-back across scan blocks).
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const PreArgs a) {
+  __shared__ unsigned long long s_wsum[SCAN_THREADS / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_blk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_blk = atomicAdd(&a.counters[CNT_PRE_TICKET], 1u);  // dynamic id: predecessors are running
+  __syncthreads();
+  const int blk = (int)s_blk;
+  const int first = blk * SCAN_TILE + tid * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  unsigned long long tsum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = first + i < a.n_tickets ? a.ticket_totals[first + i] : 0u; tsum += v[i]; }
+  unsigned long long incl = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  unsigned long long wexcl = 0, btotal = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; w++) { const unsigned long long t = s_wsum[w]; if (w < warp) wexcl += t; btotal += t; }
+  if (warp == 0) {
+    if (lane == 0) st_volatile_u64(&a.scan_blocks[blk], (blk == 0 ? SCAN_FLAG_PREFIX : SCAN_FLAG_AGG) | btotal);
+    unsigned long long excl = 0;
+    for (int idx = blk - 1; idx >= 0; idx -= 32) {
+      const int t = idx - lane;
+      uint64_t w = SCAN_FLAG_PREFIX;  // blocks < 0 count as an empty prefix
+      if (t >= 0) { do { w = ld_volatile_u64(&a.scan_blocks[t]); } while ((w >> 62) == 0); }
+      const uint32_t pmask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+      const int firstp = pmask ? (__ffs(pmask) - 1) : 32;
+      unsigned long long x = (lane <= firstp) ? (w & SCAN_VALUE_MASK) : 0ull;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+      excl += x;
       if (pmask) break;
-      idx -= 32;
     }
     if (lane == 0) {
-      if (ticket != 0) st_volatile_u64(&a.scan_state[ticket], SCAN_FLAG_PREFIX | (excl + block_total));
+      if (blk != 0) st_volatile_u64(&a.scan_blocks[blk], SCAN_FLAG_PREFIX | (excl + btotal));
       s_base = excl;
-      if (ticket == a.n_tickets - 1) {
-        const unsigned long long total = excl + block_total;
+      if ((blk + 1) * SCAN_TILE >= a.n_tickets) {  // last block: the grand total
+        const unsigned long long total = excl + btotal;
         a.status->num_pairs = total;
         a.status->overflow = total > a.pair_capacity ? 1u : 0u;
         if (a.status_host) {  // straight to the host over PCIe: no copy engine, no extra launch
@@ -248,14 +279,33 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_bin_kernel(const B200s
     }
   }
   __syncthreads();
-  const unsigned long long base = s_base;
-  if (base + block_total > a.pair_capacity) return;  // overflow: the host re-runs with a larger capacity
+  unsigned long long run = s_base + wexcl + incl - tsum;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { if (first + i < a.n_tickets) a.ticket_offsets[first + i] = run; run += v[i]; }
+}
 
-  // ---- emit (key, value) pairs -----------------------------------------------------------------
-  const unsigned long long off = base + my_excl;
-  const uint32_t dbits = __float_as_uint(depth);
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PRE_THREADS) emit_kernel(const PreArgs a) {
+  __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
+  if (a.status->overflow) return;  // the host re-runs with a larger capacity
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ticket = blockIdx.x;
+  const int view = ticket % a.VV, chunk = ticket / a.VV;
+  const uint2 info = a.bin_info[(size_t)ticket * PRE_THREADS + tid];
+  const int rx0 = info.y & 255, ry0 = (info.y >> 8) & 255, rx1 = (info.y >> 16) & 255, ry1 = info.y >> 24;
+  const uint32_t tiles = (uint32_t)((rx1 - rx0) * (ry1 - ry0));
+  uint32_t incl = tiles;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) s_warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t warp_excl = 0;
+#pragma unroll
+  for (int w = 0; w < PRE_THREADS / 32; w++) if (w < warp) warp_excl += s_warp_tot[w];
+  const unsigned long long off = a.ticket_offsets[ticket] + warp_excl + incl - tiles;
+  const uint32_t dbits = info.x;
   const uint32_t vhi = (uint32_t)view << a.tile_bits;
-  const uint32_t gidx = (uint32_t)(i0 + tid);
+  const uint32_t gidx = (uint32_t)(chunk * PRE_THREADS + tid);
   const bool big = tiles > (uint32_t)WARP_EMIT_THRESHOLD;
   if (tiles > 0 && !big) {
     unsigned long long o = off;
@@ -304,7 +354,10 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   const bool start_in_a = (plan.sort_passes % 2) == 0;
   a.keys = reinterpret_cast<uint64_t*>(scratch + (start_in_a ? plan.off_keys_a : plan.off_keys_b));
   a.vals = start_in_a ? reinterpret_cast<uint32_t*>(saved + plan.off_vals_a) : reinterpret_cast<uint32_t*>(scratch + plan.off_vals_b);
-  a.scan_state = reinterpret_cast<uint64_t*>(scratch + plan.off_scan_state);
+  a.ticket_offsets = reinterpret_cast<unsigned long long*>(scratch + plan.off_scan_state);
+  a.ticket_totals = reinterpret_cast<uint32_t*>(scratch + plan.off_ticket_totals);
+  a.scan_blocks = reinterpret_cast<uint64_t*>(scratch + plan.off_scan_blocks);
+  a.bin_info = reinterpret_cast<uint2*>(scratch + plan.off_bin_info);
   a.counters = reinterpret_cast<uint32_t*>(scratch + plan.off_counters);
   a.status = reinterpret_cast<B200sStatus*>(saved + plan.off_status);
   a.radii = out ? out->radii : nullptr;
@@ -314,15 +367,21 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   stage_mark(B200S_STAGE_PRE_BIN, stream);
   if ((e = cudaMemsetAsync(a.status, 0, sizeof(B200sStatus), stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(a.counters, 0, CNT_WORDS * sizeof(uint32_t), stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(a.scan_state, 0, (size_t)plan.pre_tickets * sizeof(uint64_t), stream)) != cudaSuccess) return e;
+  const int scan_blocks = (plan.pre_tickets + SCAN_TILE - 1) / SCAN_TILE;
+  if ((e = cudaMemsetAsync(a.scan_blocks, 0, (size_t)scan_blocks * sizeof(uint64_t), stream)) != cudaSuccess) return e;
   size_t smem = (size_t)PRE_THREADS * a.fpg * sizeof(float);
   if (smem < (size_t)PRE_THREADS * sizeof(Rec)) smem = (size_t)PRE_THREADS * sizeof(Rec);
   static thread_local size_t configured = 0;
   if (smem > configured) {
-    if ((e = cudaFuncSetAttribute(preprocess_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     configured = smem;
   }
-  if (plan.pre_tickets > 0) { preprocess_bin_kernel<<<plan.pre_tickets, PRE_THREADS, smem, stream>>>(sc, vw, a); count_launches(1); }
+  if (plan.pre_tickets > 0) {
+    project_kernel<<<plan.pre_tickets, PRE_THREADS, smem, stream>>>(sc, vw, a);
+    scan_kernel<<<scan_blocks, SCAN_THREADS, 0, stream>>>(a);
+    emit_kernel<<<plan.pre_tickets, PRE_THREADS, 0, stream>>>(a);
+    count_launches(3);
+  }
   return cudaGetLastError();
 }
 }  // namespace b200s

@@ -24,7 +24,7 @@ while [ $# -gt 0 ]; do
       shift; REGEX="$1"
       NCU_CMD="python bench.py --steps 1 --warmup 3 --no-cpu"
       $NCU_CMD > gpurun_out/ncu_plain.log 2>&1 &&
-      ncu --set full --clock-control none --import-source on -k regex:"$REGEX" -s 55 -c 14 -f -o gpurun_out/prof $NCU_CMD > gpurun_out/ncu_full.log 2>&1
+      ncu --set full --clock-control none --import-source on -k regex:"$REGEX" -s 9 -c 6 -f -o gpurun_out/prof $NCU_CMD > gpurun_out/ncu_full.log 2>&1
       echo "ncu-full rc=$?" ;;
   esac
   shift
