@@ -181,6 +181,7 @@ def run_ours(args):
     from my_depthsplat_b200 import _lib
     from my_depthsplat_b200 import rasterizer as R
     from my_depthsplat_b200.decoder_splatting_cuda import DecoderSplattingCUDACfg, get_decoder
+    from my_depthsplat_b200.dist import ViewShardedDecoder, shard_views
     from my_depthsplat_b200.scenes import CONFIGS, make_scene
     from my_depthsplat_b200.types import Gaussians
 
@@ -194,24 +195,23 @@ def run_ours(args):
     host = {
         "means": scene_cpu.gaussians.means, "covariances": scene_cpu.gaussians.covariances,
         "harmonics": scene_cpu.gaussians.harmonics, "opacities": scene_cpu.gaussians.opacities,
-        "extrinsics": scene_cpu.extrinsics[:, vs].contiguous(), "intrinsics": scene_cpu.intrinsics[:, vs].contiguous(),
-        "near": scene_cpu.near[:, vs].contiguous(), "far": scene_cpu.far[:, vs].contiguous(),
+        # cameras of ALL world*V target views (a few hundred bytes); my_depthsplat_b200.dist slices this rank's views
+        "extrinsics": scene_cpu.extrinsics.contiguous(), "intrinsics": scene_cpu.intrinsics.contiguous(),
+        "near": scene_cpu.near.contiguous(), "far": scene_cpu.far.contiguous(),
         "grad_color": scene_cpu.grad_color[:, vs].contiguous(),
     }
     host = {k: v.pin_memory() for k, v in host.items()}
     devt = {k: v.to(dev) for k, v in host.items()}
     dataset_cfg = type("DatasetCfg", (), {"background_color": [0.0, 0.0, 0.0]})()
     decoder = get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), dataset_cfg).to(dev)
+    # view sharding + ONE NCCL all-reduce of the flattened per-Gaussian gradients in the backward (identity at N=1)
+    sharded = ViewShardedDecoder(decoder)
     gnames = ("means", "covariances", "harmonics", "opacities")
 
     def step(t):
         leaves = [t[k].detach().requires_grad_() for k in gnames]
-        out = decoder.forward(Gaussians(*leaves), t["extrinsics"], t["intrinsics"], t["near"], t["far"], (H, W), depth_mode=None)
+        out = sharded.forward(Gaussians(*leaves), t["extrinsics"], t["intrinsics"], t["near"], t["far"], (H, W), depth_mode=None)
         grads = torch.autograd.grad(out.color, leaves, t["grad_color"])
-        if world > 1:  # view-sharded training: per-Gaussian gradients are summed over the ranks
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat)
-            grads = flat
         return out.color, grads
 
     host_out = {}
@@ -331,17 +331,18 @@ def run_ours(args):
     nprof = 5
     torch.cuda.synchronize()
     acc = {}
-    for _ in range(nprof):
+    for _ in range(nprof):  # one read for all steps, so that the gaps BETWEEN steps are on the record too
         step(devt)
-        for k, v in _lib.profile_read().items():
-            acc[k] = acc.get(k, 0.0) + v
+    for k, v in _lib.profile_read().items():
+        acc[k] = acc.get(k, 0.0) + v
     _lib.profile_enable(False)
     stages_ms = {k: v / nprof for k, v in acc.items()}
+    gap_ms = stages_ms.pop("end", 0.0) * nprof / max(nprof - 0.5, 1)  # between library calls: torch glue + idle
 
     # ---- work counters of one forward (pairs, visible, tested, blended) --------------------------------
     from my_depthsplat_b200.cuda_splatting import render_views
     with torch.no_grad():
-        render_views(devt["extrinsics"], devt["intrinsics"], devt["near"], devt["far"], (H, W), decoder.background_color,
+        render_views(*(shard_views(devt[k], world, rank) for k in ("extrinsics", "intrinsics", "near", "far")), (H, W), decoder.background_color,
                      devt["means"], devt["covariances"], devt["harmonics"], devt["opacities"], count_work=True)
     st = R.last_stats
     plan = _lib.plan(1, N, V, H, W, max(st.num_pairs, 1))
@@ -406,6 +407,7 @@ def run_ours(args):
             "roofline": roofline,
             "roofline_hbm": ({"kernel": dom_hbm, **hbm_stages[dom_hbm], "peak": hbm_peak} if dom_hbm else None),
             "stages": stage_report,
+            "between_calls_ms": round(gap_ms, 4),
             "work": {"pairs": Rn, "visible": Nv, "tested": st.tested, "blended": st.blended, "max_tile_len": st.max_tile_len,
                      "sort_passes": plan.sort_passes, "pixels_per_step": pix_step},
             "cpu_baseline": cpu_baseline,

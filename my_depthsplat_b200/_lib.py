@@ -166,4 +166,5 @@ def profile_read() -> dict:
     """Milliseconds per stage accumulated since the last read (synchronises on the recorded events)."""
     buf = (C.c_float * len(STAGES))()
     load().b200s_profile_read(buf)
-    return {name: float(buf[i]) for i, name in enumerate(STAGES) if name != "end"}
+    # "end" = time between the end of one library call and the first stage of the next one (host glue, gaps)
+    return {name: float(buf[i]) for i, name in enumerate(STAGES)}

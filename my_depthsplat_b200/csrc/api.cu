@@ -64,7 +64,7 @@ int b200s_profile_read(float* ms) {
   if (g_nev > 0) cudaEventSynchronize(g_ev[g_nev - 1]);
   for (int i = 0; i + 1 < g_nev; i++) {
     float t = 0.f;
-    if (g_ev_stage[i] != B200S_STAGE_END && cudaEventElapsedTime(&t, g_ev[i], g_ev[i + 1]) == cudaSuccess) { ms[g_ev_stage[i]] += t; seen++; }
+    if (cudaEventElapsedTime(&t, g_ev[i], g_ev[i + 1]) == cudaSuccess) { ms[g_ev_stage[i]] += t; seen++; }
   }
   g_nev = 0;
   return seen;

@@ -25,9 +25,23 @@ def inverse_nosync(m: Tensor) -> Tensor:
     return torch.linalg.inv_ex(m, check_errors=False).inverse
 
 
+_pixel_cache: dict = {}
+
+
+def _edge_pixel(device, u: float, v: float) -> Tensor:
+    """Homogeneous edge mid-point as a device tensor, created once per device: building it per call
+    (``torch.tensor(..., device=cuda)``) is a pageable host->device copy that SYNCHRONISES the stream, i.e.
+    stalls the host until the previous step's kernels have drained and exposes every following launch."""
+    key = (device, u, v)
+    t = _pixel_cache.get(key)
+    if t is None:
+        t = torch.tensor([u, v, 1.0], dtype=torch.float32, device=device)
+        _pixel_cache[key] = t
+    return t
+
+
 def _unit_ray(k_inv: Tensor, u: float, v: float) -> Tensor:
-    pixel = torch.tensor([u, v, 1.0], dtype=torch.float32, device=k_inv.device)
-    ray = torch.einsum("bij,j->bi", k_inv, pixel)
+    ray = torch.einsum("bij,j->bi", k_inv, _edge_pixel(k_inv.device, u, v))
     return ray / ray.norm(dim=-1, keepdim=True)
 
 
