@@ -180,7 +180,8 @@ int b200s_forward_render(const B200sScene* sc, const B200sViews* vw, const B200s
   uint32_t* vals_a = reinterpret_cast<uint32_t*>(saved + pl->off_vals_a);
   uint32_t* vals_b = reinterpret_cast<uint32_t*>(scratch + pl->off_vals_b);
   cudaError_t e = launch_sort(keys_a, vals_a, keys_b, vals_b, pl->sort_passes, pl->pair_capacity, cnt, reinterpret_cast<uint32_t*>(scratch + pl->off_hist),
-                              reinterpret_cast<uint32_t*>(scratch + pl->off_lookback), reinterpret_cast<uint32_t*>(scratch + pl->off_counters), sm_count(), stream);
+                              reinterpret_cast<uint32_t*>(scratch + pl->off_lookback), reinterpret_cast<uint32_t*>(scratch + pl->off_counters), sm_count(), stream,
+                              /*hist_ready=*/true);
   if (e != cudaSuccess) return fail(e);
   uint2* ranges = reinterpret_cast<uint2*>(saved + pl->off_ranges);
   e = launch_tile_ranges(keys_a, cnt, ranges, pl->bins, pl->pair_capacity, sm_count(), stream);
@@ -249,7 +250,7 @@ int b200s_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint3
     if (e != cudaSuccess) return fail(e);
   }
   CountRef cnt{nullptr, nullptr, (unsigned long long)n};
-  const cudaError_t e = launch_sort(keys_a, vals_a, keys_b, vals_b, passes, n, cnt, hist, lookback, counters, sm_count(), s);
+  const cudaError_t e = launch_sort(keys_a, vals_a, keys_b, vals_b, passes, n, cnt, hist, lookback, counters, sm_count(), s, /*hist_ready=*/false);
   return e == cudaSuccess ? B200S_OK : fail(e);
 }
 

@@ -39,6 +39,8 @@ struct PreArgs {
   uint32_t* ticket_totals;          // [n_tickets]
   unsigned long long* ticket_offsets;  // [n_tickets] exclusive scan of the totals
   uint64_t* scan_blocks;            // [scan blocks] decoupled look-back words
+  uint32_t* hist;                   // [8*256] digit histograms of the sort (accumulated by emit_kernel)
+  int sort_passes;
   uint32_t* counters;
   B200sStatus* status;
   int32_t* radii;
@@ -285,52 +287,74 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const PreArgs a) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// Persistent: gridDim.x CTAs loop over the tickets, so that the per-CTA digit histograms (all sort passes,
+// accumulated in shared memory while the keys are being written) are flushed with few global atomics.
+// A Gaussian's pairs share their depth bits, so the four depth digits cost one shared atomic per GAUSSIAN
+// (adding its tile count); the (view | tile) digits cost one per pair.  This removes the sort's separate
+// histogram pass over the keys (8 B per pair re-read).
 __global__ void __launch_bounds__(PRE_THREADS) emit_kernel(const PreArgs a) {
   __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
+  __shared__ uint32_t s_hist[8][256];
   if (a.status->overflow) return;  // the host re-runs with a larger capacity
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ticket = blockIdx.x;
-  const int view = ticket % a.VV, chunk = ticket / a.VV;
-  const uint2 info = a.bin_info[(size_t)ticket * PRE_THREADS + tid];
-  const int rx0 = info.y & 255, ry0 = (info.y >> 8) & 255, rx1 = (info.y >> 16) & 255, ry1 = info.y >> 24;
-  const uint32_t tiles = (uint32_t)((rx1 - rx0) * (ry1 - ry0));
-  uint32_t incl = tiles;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-  if (lane == 31) s_warp_tot[warp] = incl;
+  for (int p = 0; p < 8; p++) s_hist[p][tid] = 0;
   __syncthreads();
-  uint32_t warp_excl = 0;
+  const int hi_passes = a.sort_passes - 4;
+  for (int ticket = blockIdx.x; ticket < a.n_tickets; ticket += gridDim.x) {
+    const int view = ticket % a.VV, chunk = ticket / a.VV;
+    const uint2 info = a.bin_info[(size_t)ticket * PRE_THREADS + tid];
+    const int rx0 = info.y & 255, ry0 = (info.y >> 8) & 255, rx1 = (info.y >> 16) & 255, ry1 = info.y >> 24;
+    const uint32_t tiles = (uint32_t)((rx1 - rx0) * (ry1 - ry0));
+    uint32_t incl = tiles;
 #pragma unroll
-  for (int w = 0; w < PRE_THREADS / 32; w++) if (w < warp) warp_excl += s_warp_tot[w];
-  const unsigned long long off = a.ticket_offsets[ticket] + warp_excl + incl - tiles;
-  const uint32_t dbits = info.x;
-  const uint32_t vhi = (uint32_t)view << a.tile_bits;
-  const uint32_t gidx = (uint32_t)(chunk * PRE_THREADS + tid);
-  const bool big = tiles > (uint32_t)WARP_EMIT_THRESHOLD;
-  if (tiles > 0 && !big) {
-    unsigned long long o = off;
-    for (int y = ry0; y < ry1; y++)
-      for (int x = rx0; x < rx1; x++) {
-        a.keys[o] = ((uint64_t)(vhi | (uint32_t)(y * a.grid_x + x)) << 32) | dbits;
-        a.vals[o] = gidx;
-        o++;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    __syncthreads();  // previous ticket's readers of s_warp_tot are done
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t warp_excl = 0;
+#pragma unroll
+    for (int w = 0; w < PRE_THREADS / 32; w++) if (w < warp) warp_excl += s_warp_tot[w];
+    const unsigned long long off = a.ticket_offsets[ticket] + warp_excl + incl - tiles;
+    const uint32_t dbits = info.x;
+    const uint32_t vhi = (uint32_t)view << a.tile_bits;
+    const uint32_t gidx = (uint32_t)(chunk * PRE_THREADS + tid);
+    const bool big = tiles > (uint32_t)WARP_EMIT_THRESHOLD;
+    if (tiles > 0) {
+#pragma unroll
+      for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p][(dbits >> (8 * p)) & 255u], tiles);
+    }
+    if (tiles > 0 && !big) {
+      unsigned long long o = off;
+      for (int y = ry0; y < ry1; y++)
+        for (int x = rx0; x < rx1; x++) {
+          const uint32_t hi = vhi | (uint32_t)(y * a.grid_x + x);
+          a.keys[o] = ((uint64_t)hi << 32) | dbits;
+          a.vals[o] = gidx;
+          o++;
+          for (int hp = 0; hp < hi_passes; hp++) atomicAdd(&s_hist[4 + hp][(hi >> (8 * hp)) & 255u], 1u);
+        }
+    }
+    uint32_t bmask = __ballot_sync(0xffffffffu, big);
+    while (bmask) {
+      const int src = __ffs(bmask) - 1;
+      bmask &= bmask - 1;
+      const int x0 = __shfl_sync(0xffffffffu, rx0, src), y0 = __shfl_sync(0xffffffffu, ry0, src);
+      const int w = __shfl_sync(0xffffffffu, rx1, src) - x0;
+      const uint32_t cnt = __shfl_sync(0xffffffffu, tiles, src);
+      const unsigned long long o = __shfl_sync(0xffffffffu, off, src);
+      const uint32_t db = __shfl_sync(0xffffffffu, dbits, src), gi = __shfl_sync(0xffffffffu, gidx, src);
+      for (uint32_t k = lane; k < cnt; k += 32) {
+        const int yy = y0 + (int)(k / (uint32_t)w), xx = x0 + (int)(k % (uint32_t)w);
+        const uint32_t hi = vhi | (uint32_t)(yy * a.grid_x + xx);
+        a.keys[o + k] = ((uint64_t)hi << 32) | db;
+        a.vals[o + k] = gi;
+        for (int hp = 0; hp < hi_passes; hp++) atomicAdd(&s_hist[4 + hp][(hi >> (8 * hp)) & 255u], 1u);
       }
-  }
-  uint32_t bmask = __ballot_sync(0xffffffffu, big);
-  while (bmask) {
-    const int src = __ffs(bmask) - 1;
-    bmask &= bmask - 1;
-    const int x0 = __shfl_sync(0xffffffffu, rx0, src), y0 = __shfl_sync(0xffffffffu, ry0, src);
-    const int w = __shfl_sync(0xffffffffu, rx1, src) - x0;
-    const uint32_t cnt = __shfl_sync(0xffffffffu, tiles, src);
-    const unsigned long long o = __shfl_sync(0xffffffffu, off, src);
-    const uint32_t db = __shfl_sync(0xffffffffu, dbits, src), gi = __shfl_sync(0xffffffffu, gidx, src);
-    for (uint32_t k = lane; k < cnt; k += 32) {
-      const int yy = y0 + (int)(k / (uint32_t)w), xx = x0 + (int)(k % (uint32_t)w);
-      a.keys[o + k] = ((uint64_t)(vhi | (uint32_t)(yy * a.grid_x + xx)) << 32) | db;
-      a.vals[o + k] = gi;
     }
   }
+  __syncthreads();
+  for (int p = 0; p < a.sort_passes; p++) { const uint32_t c = s_hist[p][tid]; if (c) atomicAdd(&a.hist[p * 256 + tid], c); }
 }
 
 }  // namespace b200s
@@ -358,6 +382,8 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   a.ticket_totals = reinterpret_cast<uint32_t*>(scratch + plan.off_ticket_totals);
   a.scan_blocks = reinterpret_cast<uint64_t*>(scratch + plan.off_scan_blocks);
   a.bin_info = reinterpret_cast<uint2*>(scratch + plan.off_bin_info);
+  a.hist = reinterpret_cast<uint32_t*>(scratch + plan.off_hist);
+  a.sort_passes = plan.sort_passes;
   a.counters = reinterpret_cast<uint32_t*>(scratch + plan.off_counters);
   a.status = reinterpret_cast<B200sStatus*>(saved + plan.off_status);
   a.radii = out ? out->radii : nullptr;
@@ -369,6 +395,7 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   if ((e = cudaMemsetAsync(a.counters, 0, CNT_WORDS * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   const int scan_blocks = (plan.pre_tickets + SCAN_TILE - 1) / SCAN_TILE;
   if ((e = cudaMemsetAsync(a.scan_blocks, 0, (size_t)scan_blocks * sizeof(uint64_t), stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(a.hist, 0, 8 * 256 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   size_t smem = (size_t)PRE_THREADS * a.fpg * sizeof(float);
   if (smem < (size_t)PRE_THREADS * sizeof(Rec)) smem = (size_t)PRE_THREADS * sizeof(Rec);
   static thread_local size_t configured = 0;
@@ -379,7 +406,11 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   if (plan.pre_tickets > 0) {
     project_kernel<<<plan.pre_tickets, PRE_THREADS, smem, stream>>>(sc, vw, a);
     scan_kernel<<<scan_blocks, SCAN_THREADS, 0, stream>>>(a);
-    emit_kernel<<<plan.pre_tickets, PRE_THREADS, 0, stream>>>(a);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int emit_blocks = plan.pre_tickets < sms * 6 ? plan.pre_tickets : sms * 6;
+    emit_kernel<<<emit_blocks, PRE_THREADS, 0, stream>>>(a);
     count_launches(3);
   }
   return cudaGetLastError();

@@ -311,11 +311,12 @@ int sort_tiles_for(long long n_cap) { return (int)((n_cap + SORT_TILE - 1) / SOR
 // Sorts on the low `passes*8` bits.  Input in (keys_in, vals_in) = A if passes is even, else B;
 // the output always ends in the A buffers.  hist [8*256], lookback [2*tiles*256], counters [CNT_WORDS].
 cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int passes, long long n_cap,
-                        CountRef cnt, uint32_t* hist, uint32_t* lookback, uint32_t* counters, int sm_count, cudaStream_t stream) {
+                        CountRef cnt, uint32_t* hist, uint32_t* lookback, uint32_t* counters, int sm_count, cudaStream_t stream,
+                        bool hist_ready) {
   if (passes <= 0 || n_cap <= 0) return cudaSuccess;
   cudaError_t e;
   const int tiles = sort_tiles_for(n_cap);
-  if ((e = cudaMemsetAsync(hist, 0, 8 * RADIX * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+  if (!hist_ready && (e = cudaMemsetAsync(hist, 0, 8 * RADIX * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(counters + CNT_SORT_TILE0, 0, 8 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   const bool start_in_a = (passes % 2) == 0;
@@ -335,11 +336,14 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     stage_mark(B200S_STAGE_SORT_HIST, stream);
-    if (g_sort_knobs[0] == 0) digit_histogram_kernel<0><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
-    else if (g_sort_knobs[0] == 1) digit_histogram_kernel<1><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
-    else digit_histogram_kernel<2><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+    if (!hist_ready) {  // forward computes the histograms while it emits the keys (emit_kernel); the stand-alone sort reads them here
+      if (g_sort_knobs[0] == 0) digit_histogram_kernel<0><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+      else if (g_sort_knobs[0] == 1) digit_histogram_kernel<1><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+      else digit_histogram_kernel<2><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+      count_launches(1);
+    }
     digit_scan_kernel<<<1, RADIX, 0, stream>>>(hist, passes);
-    count_launches(2);
+    count_launches(1);
   }
   stage_mark(B200S_STAGE_SORT_PASSES, stream);
   {
