@@ -166,44 +166,49 @@ struct PixState {
   uint32_t last_contributor;
 };
 
-// one list entry on one pixel; writes its 10 partial gradients to out[0..9]
+// One list entry on the warp's 32 pixels; writes this pixel's 10 partial gradients to out[0..9].
+// Returns (warp-uniform) whether ANY pixel of the warp received a contribution: a quarter of the entries
+// that pass the bounding-box cull touch no pixel that is still "alive" at that list position, and they are
+// dropped before the cross-lane reduction.  All 32 lanes must call.
 // h0 = (x, y, ex, ey)  h1 = (A, B, C, opacity)  h2 = (r, g, b, zc)
 template <bool DEPTH>
-__device__ __forceinline__ void bwd_entry(const float4 h0, const float4 h1, const float4 h2, const uint32_t pos, PixState<DEPTH>& s,
+__device__ __forceinline__ bool bwd_entry(const float4 h0, const float4 h1, const float4 h2, const uint32_t pos, PixState<DEPTH>& s,
                                           const TileGeom& g, const float half_w, const float half_h, float* out) {
-#pragma unroll
-  for (int k = 0; k < 10; k++) out[k] = 0.f;
-  if (pos >= s.last_contributor) return;
   const float dx = __fsub_rn(h0.x, g.pfx), dy = __fsub_rn(h0.y, g.pfy);
   const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
-  if (power > 0.0f) return;
   const float G = expf(power);
   const float alpha = fminf(ALPHA_MAX, __fmul_rn(h1.w, G));
-  if (alpha < ALPHA_MIN) return;
-  s.T = s.T / (1.f - alpha);
-  const float w = alpha * s.T;
-  const float col[4] = {h2.x, h2.y, h2.z, h2.w};
-  float dL_dalpha = 0.f;
+  const bool live = pos < s.last_contributor && power <= 0.0f && alpha >= ALPHA_MIN;
+  if (!__any_sync(0xffffffffu, live)) return false;
 #pragma unroll
-  for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) {
-    s.accum[ch] = s.last_alpha * s.last_col[ch] + (1.f - s.last_alpha) * s.accum[ch];
-    s.last_col[ch] = col[ch];
-    dL_dalpha += (col[ch] - s.accum[ch]) * s.dpix[ch];
-    out[6 + ch] = w * s.dpix[ch];
+  for (int k = 0; k < 10; k++) out[k] = 0.f;
+  if (live) {
+    const float inv = __fdividef(1.f, 1.f - alpha);
+    s.T = s.T * inv;
+    const float w = alpha * s.T;
+    const float col[4] = {h2.x, h2.y, h2.z, h2.w};
+    float dL_dalpha = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) {
+      s.accum[ch] = s.last_alpha * s.last_col[ch] + (1.f - s.last_alpha) * s.accum[ch];
+      s.last_col[ch] = col[ch];
+      dL_dalpha += (col[ch] - s.accum[ch]) * s.dpix[ch];
+      out[6 + ch] = w * s.dpix[ch];
+    }
+    dL_dalpha *= s.T;
+    s.last_alpha = alpha;
+    dL_dalpha -= s.T_final * inv * s.bg_dot;
+    const float dL_dG = h1.w * dL_dalpha;
+    const float gdx = G * dx, gdy = G * dy;
+    out[0] = dL_dG * (-gdx * h1.x - gdy * h1.y) * half_w;
+    out[1] = dL_dG * (-gdy * h1.z - gdx * h1.y) * half_h;
+    const float m = -0.5f * dL_dG;
+    out[2] = m * gdx * dx;
+    out[3] = m * gdx * dy;
+    out[4] = m * gdy * dy;
+    out[5] = G * dL_dalpha;
   }
-  dL_dalpha *= s.T;
-  s.last_alpha = alpha;
-  dL_dalpha += (-s.T_final / (1.f - alpha)) * s.bg_dot;
-  const float dL_dG = h1.w * dL_dalpha;
-  const float gdx = G * dx, gdy = G * dy;
-  const float dG_ddelx = -gdx * h1.x - gdy * h1.y;
-  const float dG_ddely = -gdy * h1.z - gdx * h1.y;
-  out[0] = dL_dG * dG_ddelx * half_w;
-  out[1] = dL_dG * dG_ddely * half_h;
-  out[2] = -0.5f * gdx * dx * dL_dG;
-  out[3] = -0.5f * gdx * dy * dL_dG;
-  out[4] = -0.5f * gdy * dy * dL_dG;
-  out[5] = G * dL_dalpha;
+  return true;
 }
 
 template <bool DEPTH>
@@ -271,26 +276,32 @@ __global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_kernel(const CompAr
     }
     __syncwarp();
     const int nh = __popc(mask);
-    for (int k0 = 0; k0 < nh; k0 += 3) {
+    // batches of three NON-EMPTY entries: walk the compacted slots in order, keep an entry only if some pixel
+    // of the warp received a contribution from it
+    for (int k = 0; k < nh;) {
       float v[32];
-      uint32_t ids[3];
+      uint32_t id0 = 0xffffffffu, id1 = 0xffffffffu, id2 = 0xffffffffu;
+      bool f = false;
+      while (k < nh && !f) { f = bwd_entry<DEPTH>(s_q0[warp][k], s_q1[warp][k], s_q2[warp][k], s_pos[warp][k], s, g, half_w, half_h, v); if (f) id0 = s_id[warp][k]; k++; }
+      if (!f) break;
+      f = false;
+      while (k < nh && !f) { f = bwd_entry<DEPTH>(s_q0[warp][k], s_q1[warp][k], s_q2[warp][k], s_pos[warp][k], s, g, half_w, half_h, v + 10); if (f) id1 = s_id[warp][k]; k++; }
+      if (!f) {
 #pragma unroll
-      for (int e = 0; e < 3; e++) {
-        if (k0 + e < nh) {  // warp-uniform
-          ids[e] = s_id[warp][k0 + e];
-          bwd_entry<DEPTH>(s_q0[warp][k0 + e], s_q1[warp][k0 + e], s_q2[warp][k0 + e], s_pos[warp][k0 + e], s, g, half_w, half_h, v + 10 * e);
-        } else {
-          ids[e] = 0xffffffffu;
+        for (int i = 10; i < 20; i++) v[i] = 0.f;
+      }
+      f = false;
+      while (k < nh && !f) { f = bwd_entry<DEPTH>(s_q0[warp][k], s_q1[warp][k], s_q2[warp][k], s_pos[warp][k], s, g, half_w, half_h, v + 20); if (f) id2 = s_id[warp][k]; k++; }
+      if (!f) {
 #pragma unroll
-          for (int k = 0; k < 10; k++) v[10 * e + k] = 0.f;
-        }
+        for (int i = 20; i < 30; i++) v[i] = 0.f;
       }
       v[30] = 0.f; v[31] = 0.f;
       butterfly_step<16>(v, lane); butterfly_step<8>(v, lane); butterfly_step<4>(v, lane);
       butterfly_step<2>(v, lane); butterfly_step<1>(v, lane);
-      const int e = lane / 10, k = lane - 10 * e;
-      const uint32_t gid = e == 0 ? ids[0] : (e == 1 ? ids[1] : (e == 2 ? ids[2] : 0xffffffffu));
-      if (gid != 0xffffffffu && v[0] != 0.f) atomicAdd(grec + (size_t)gid * GREC_FLOATS + k, v[0]);
+      const int e = lane / 10, c = lane - 10 * e;
+      const uint32_t gid = e == 0 ? id0 : (e == 1 ? id1 : (e == 2 ? id2 : 0xffffffffu));
+      if (gid != 0xffffffffu && v[0] != 0.f) atomicAdd(grec + (size_t)gid * GREC_FLOATS + c, v[0]);
     }
     __syncwarp();  // slot reads of this chunk are done before the next chunk overwrites them
   }
