@@ -88,7 +88,7 @@ __device__ __forceinline__ float eval_sh_channel(int deg, const float* sh, int k
   return r;
 }
 
-__global__ void __launch_bounds__(PRE_THREADS) project_kernel(const B200sScene sc, const B200sViews vw, const PreArgs a) {
+__global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScene sc, const B200sViews vw, const PreArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ ViewParams vp;
   __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];

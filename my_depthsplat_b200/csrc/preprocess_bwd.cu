@@ -52,7 +52,7 @@ __device__ __forceinline__ void dnormvdv(const float v[3], const float dv[3], fl
 
 // NC = SH coefficients per channel that are ACTIVE ((deg+1)^2); NC == 0 -> colors_precomp path.
 template <int NC>
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_bwd_kernel(const B200sScene sc, const B200sViews vw, const B200sGradIn gin,
+__global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B200sScene sc, const B200sViews vw, const B200sGradIn gin,
                                                                      const PreBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ ViewParams vp;
