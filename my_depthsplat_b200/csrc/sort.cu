@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const Pa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
 #pragma unroll
-  for (int w = 0; w < SORT_WARPS; w++) { s_wc[w][tid] = 0; if (RMODE == 3) s_vout[w * RADIX + tid] = 0; }
+  for (int w = 0; w < SORT_WARPS; w++) { s_wc[w][tid] = 0; if (RMODE >= 3) s_vout[w * RADIX + tid] = 0; }
   __syncthreads();
   const uint32_t tile = s_tile;
   const unsigned long long base = (unsigned long long)tile * SORT_TILE;
@@ -192,6 +192,29 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const Pa
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t* wc = s_wc[warp];
   uint32_t* mm = s_vout + warp * RADIX;  // RMODE 3: per-warp match masks (s_vout is idle until the very end)
+  if (RMODE == 4) {
+    // Two independent ranking chains per warp (items 0..7 against `wc`, items 8..15 against a second counter
+    // array parked in the idle s_vout region): the read-count / leader-update round trip through shared
+    // memory is the serial part of the loop, and two chains in flight halve it.  Chain A matches with ballots
+    // (ALU pipe), chain B with MATCH.ANY (ADU pipe).
+    uint32_t* wcB = s_vout + warp * RADIX;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS / 2; i++) {
+      const uint32_t dA = (uint32_t)(key[i] >> a.shift) & 255u, dB = (uint32_t)(key[i + SORT_ITEMS / 2] >> a.shift) & 255u;
+      const uint32_t pB = match_digit<1>(dB);
+      const uint32_t pA = match_digit<0>(dA);
+      const uint32_t rA = wc[dA], rB = wcB[dB];
+      __syncwarp();
+      if (lane == (__ffs(pA) - 1)) wc[dA] = rA + __popc(pA);
+      if (lane == (__ffs(pB) - 1)) wcB[dB] = rB + __popc(pB);
+      __syncwarp();
+      rank[i] = rA + __popc(pA & lt);
+      rank[i + SORT_ITEMS / 2] = rB + __popc(pB & lt);
+    }
+    // chain A's items precede chain B's in tile order: B ranks shift by A's count of the same digit
+#pragma unroll
+    for (int i = SORT_ITEMS / 2; i < SORT_ITEMS; i++) rank[i] += wc[(uint32_t)(key[i] >> a.shift) & 255u];
+  } else
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const uint32_t d = (uint32_t)(key[i] >> a.shift) & 255u;
@@ -213,7 +236,11 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const Pa
   // ---- thread = digit: exclusive scan over warps, tile count, chained scan across tiles
   uint32_t run = 0;
 #pragma unroll
-  for (int w = 0; w < SORT_WARPS; w++) { const uint32_t t = s_wc[w][tid]; s_wc[w][tid] = run; run += t; }
+  for (int w = 0; w < SORT_WARPS; w++) {
+    const uint32_t t = s_wc[w][tid] + (RMODE == 4 ? s_vout[w * RADIX + tid] : 0u);
+    s_wc[w][tid] = run;
+    run += t;
+  }
   uint32_t prev = 0;
   {
     uint32_t* row = a.lb_cur + (size_t)tile * RADIX + tid;
@@ -353,6 +380,7 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
       if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
       if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
       if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
       sweep_configured = true;
     }
   }
@@ -368,7 +396,8 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     if (g_sort_knobs[1] == 0) onesweep_pass_kernel<0><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
     else if (g_sort_knobs[1] == 1) onesweep_pass_kernel<1><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
     else if (g_sort_knobs[1] == 2) onesweep_pass_kernel<2><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
-    else onesweep_pass_kernel<3><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
+    else if (g_sort_knobs[1] == 3) onesweep_pass_kernel<3><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
+    else onesweep_pass_kernel<4><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
     count_launches(1);
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;

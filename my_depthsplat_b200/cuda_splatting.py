@@ -26,7 +26,7 @@ from torch import Tensor
 
 from . import _lib
 from .projection import get_fov, homogenize_points, inverse_nosync
-from .rasterizer import ViewPack, rasterize
+from .rasterizer import PairLimitExceeded, ViewPack, rasterize
 
 DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
 
@@ -89,6 +89,31 @@ def render_views(
     B, V = extrinsics.shape[:2]
     h, w = image_shape
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    try:
+        return _render_views_once(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
+                                  gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh,
+                                  depth_mode, want_radii, count_work)
+    except PairLimitExceeded:
+        if V == 1:
+            raise
+    # more than 2^30 (tile, Gaussian) pairs in one call (huge Gaussians, many views): split the views and
+    # concatenate -- each half is its own autograd node, gradients add up as usual
+    half = V // 2
+    bgs = (background_color, background_color) if background_color.dim() == 1 else (background_color[:, :half], background_color[:, half:])
+    parts = [render_views(extrinsics[:, sl], intrinsics[:, sl], near[:, sl], far[:, sl], image_shape, bg, gaussian_means,
+                          gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode,
+                          want_radii, count_work) for sl, bg in zip((slice(0, half), slice(half, V)), bgs)]
+    out = [torch.cat([p[0] for p in parts], dim=1),
+           None if parts[0][1] is None else torch.cat([p[1] for p in parts], dim=1)]
+    if want_radii:
+        out.append(torch.cat([p[2] for p in parts], dim=1))
+    return tuple(out)
+
+
+def _render_views_once(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means, gaussian_covariances,
+                       gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode, want_radii, count_work):
+    B, V = extrinsics.shape[:2]
+    h, w = image_shape
     dev = gaussian_means.device
     ext = extrinsics.reshape(B * V, 4, 4).to(torch.float32)
     K = intrinsics.reshape(B * V, 3, 3).to(torch.float32)

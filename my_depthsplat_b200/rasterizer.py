@@ -59,6 +59,10 @@ debug_keep = False
 debug_last: Optional[dict] = None
 
 
+class PairLimitExceeded(RuntimeError):
+    """One call would produce more than 2^30 (tile, Gaussian) pairs; render fewer views per call."""
+
+
 class _HostStatusRing:
     """64 slots of 16 bytes of mapped pinned host memory that stage A writes the pair count into."""
     SLOTS = 64
@@ -223,7 +227,7 @@ class _Rasterize(torch.autograd.Function):
             words[2 * slot] = 0
             words[2 * slot + 1] = 0
             if num_pairs >= (1 << 30) - 1:
-                raise RuntimeError(f"{num_pairs} (tile, Gaussian) pairs in one call exceed the 2^30 limit; render fewer views per call")
+                raise PairLimitExceeded(f"{num_pairs} (tile, Gaussian) pairs in one call exceed the 2^30 limit; render fewer views per call")
             cap = min(int(num_pairs * 1.25) + 4096, (1 << 30) - 1)
             retries += 1
         _capacity_hint[key] = min(max(int(num_pairs * 1.25) + 4096, 1 << 16), (1 << 30) - 1)
