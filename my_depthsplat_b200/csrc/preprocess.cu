@@ -88,141 +88,157 @@ __device__ __forceinline__ float eval_sh_channel(int deg, const float* sh, int k
   return r;
 }
 
+// SPECIALISED = the layout DepthSplat hands over (3x3 covariances, SH [N,3,9] channel-major, degree 2):
+// every stride is a compile-time constant.  The generic instantiation takes them from the arguments.
+template <bool SPECIALISED>
 __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScene sc, const B200sViews vw, const PreArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ ViewParams vp;
   __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
 
+  const int cov_floats = SPECIALISED ? 9 : a.cov_floats;
+  const int col_floats = SPECIALISED ? 27 : a.col_floats;
+  const int col_stride = SPECIALISED ? 27 : a.col_stride;
+  const int cstride = SPECIALISED ? 9 : ((sc.sh_layout == B200S_SH_CHANNEL_MAJOR) ? sc.sh_coeffs : 1);
+  const int kstride = SPECIALISED ? 1 : ((sc.sh_layout == B200S_SH_CHANNEL_MAJOR) ? 1 : 3);
+  const int deg = SPECIALISED ? 2 : sc.sh_degree;
+  const bool precomp = SPECIALISED ? false : (sc.colors_precomp != nullptr);
+
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ticket = blockIdx.x;  // view-fastest: ticket = chunk * VV + view
-  const int view = ticket % a.VV, chunk = ticket / a.VV;
-  if (tid == 0) load_view_params(vp, vw, view, a.H, a.W);
-  __syncthreads();
-  const int scene = vp.scene;
+  const int chunk = blockIdx.x % a.chunks, scene = blockIdx.x / a.chunks;
   const int i0 = chunk * PRE_THREADS;
   const int n = min(PRE_THREADS, a.N - i0);
   const long long g0 = (long long)scene * a.N + i0;
 
-  // ---- stage the Gaussian chunk --------------------------------------------------------------
+  // ---- stage the Gaussian chunk ONCE for all the views of its scene ------------------------------
   float* s_mean = smem;                                  // [256*3]
   float* s_cov = s_mean + PRE_THREADS * 3;               // [256*cov_floats]
-  float* s_op = s_cov + PRE_THREADS * a.cov_floats;      // [256]
+  float* s_op = s_cov + PRE_THREADS * cov_floats;        // [256]
   float* s_col = s_op + PRE_THREADS;                     // [256*col_stride]
+  float4* s_rec = reinterpret_cast<float4*>(s_col + PRE_THREADS * col_stride);  // [256*4] record staging
   stage_in(s_mean, sc.means + g0 * 3, n * 3);
-  stage_in(s_cov, sc.covariances + g0 * a.cov_floats, n * a.cov_floats);
+  stage_in(s_cov, sc.covariances + g0 * cov_floats, n * cov_floats);
   stage_in(s_op, sc.opacities + g0, n);
-  const float* col_src = sc.colors_precomp ? sc.colors_precomp : sc.harmonics;
-  stage_in_padded(s_col, col_src + g0 * a.col_floats, n * a.col_floats, a.col_floats, a.col_stride);
+  const float* col_src = precomp ? sc.colors_precomp : sc.harmonics;
+  stage_in_padded(s_col, col_src + g0 * col_floats, n * col_floats, col_floats, col_stride);
   __syncthreads();
-
-  // ---- per-Gaussian projection ---------------------------------------------------------------
-  Rec out;
-  out.q0 = make_float4(0.f, 0.f, -1e30f, -1e30f); out.q1 = make_float4(0.f, 0.f, 0.f, 0.f); out.q2 = out.q1; out.q3 = out.q1;
-  uint32_t tiles = 0;
-  int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
-  float depth = 0.f;
+  float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, opac = 0.f;
   if (tid < n) {
-    const float mraw[3] = {s_mean[tid * 3], s_mean[tid * 3 + 1], s_mean[tid * 3 + 2]};
-    const float m[3] = {__fmul_rn(mraw[0], vp.s), __fmul_rn(mraw[1], vp.s), __fmul_rn(mraw[2], vp.s)};
-    const float phx = xform_row(vp.proj, 0, m[0], m[1], m[2]);
-    const float phy = xform_row(vp.proj, 1, m[0], m[1], m[2]);
-    const float phw = xform_row(vp.proj, 3, m[0], m[1], m[2]);
-    const float pw = __frcp_rn(__fadd_rn(phw, 0.0000001f));
-    const float ppx = __fmul_rn(phx, pw), ppy = __fmul_rn(phy, pw);
-    const float pvz = xform_row(vp.view, 2, m[0], m[1], m[2]);
-    if (pvz > NEAR_CULL) {
-      float c6[6];
-      const float* cp = s_cov + tid * a.cov_floats;
-      if (a.cov_floats == 6) {
+    mraw[0] = s_mean[tid * 3]; mraw[1] = s_mean[tid * 3 + 1]; mraw[2] = s_mean[tid * 3 + 2];
+    const float* cp = s_cov + tid * cov_floats;
+    if (cov_floats == 6) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) c6[k] = __fmul_rn(cp[k], vp.s2);
-      } else {
-        c6[0] = __fmul_rn(cp[0], vp.s2); c6[1] = __fmul_rn(cp[1], vp.s2); c6[2] = __fmul_rn(cp[2], vp.s2);
-        c6[3] = __fmul_rn(cp[4], vp.s2); c6[4] = __fmul_rn(cp[5], vp.s2); c6[5] = __fmul_rn(cp[8], vp.s2);
-      }
-      Cov2D q;
-      compute_cov2d(m, c6, vp, q);
-      const float det = __fsub_rn(__fmul_rn(q.a, q.c), __fmul_rn(q.b, q.b));
-      if (det != 0.0f) {
-        const float det_inv = __frcp_rn(det);
-        const float mid = __fmul_rn(0.5f, __fadd_rn(q.a, q.c));
-        const float disc = __fsqrt_rn(fmaxf(LAMBDA_FLOOR, __fsub_rn(__fmul_rn(mid, mid), det)));
-        const float lam = fmaxf(__fadd_rn(mid, disc), __fsub_rn(mid, disc));
-        const float radf = ceilf(__fmul_rn(3.f, __fsqrt_rn(lam)));
-        const int radius = (int)radf;
-        const float px = ndc2pix(ppx, a.W), py = ndc2pix(ppy, a.H);
-        get_rect(px, py, radius, a.grid_x, a.grid_y, rx0, ry0, rx1, ry1);
-        tiles = (uint32_t)((rx1 - rx0) * (ry1 - ry0));
-        if (tiles > 0) {
-          depth = pvz;
-          const float opac = s_op[tid];
-          float rgb[3];
-          uint32_t flags = 0;
-          const float* cs = s_col + tid * a.col_stride;
-          if (sc.colors_precomp) {
-            rgb[0] = cs[0]; rgb[1] = cs[1]; rgb[2] = cs[2];
-          } else {
-            float dx = m[0] - vp.campos[0], dy = m[1] - vp.campos[1], dz = m[2] - vp.campos[2];
-            const float len = __fsqrt_rn(dot3c(dx, dx, dy, dy, dz, dz));
-            dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
-            const int cstride = (sc.sh_layout == B200S_SH_CHANNEL_MAJOR) ? sc.sh_coeffs : 1;
-            const int kstride = (sc.sh_layout == B200S_SH_CHANNEL_MAJOR) ? 1 : 3;
+      for (int k = 0; k < 6; k++) craw[k] = cp[k];
+    } else {
+      craw[0] = cp[0]; craw[1] = cp[1]; craw[2] = cp[2]; craw[3] = cp[4]; craw[4] = cp[5]; craw[5] = cp[8];
+    }
+    opac = s_op[tid];
+  }
+  const float* cs = s_col + tid * col_stride;
+
+  for (int view = 0; view < a.VV; view++) {
+    if (vw.scene_index[view] != scene) continue;  // block-uniform
+    __syncthreads();  // the previous view's readers of vp / s_rec / s_warp_tot are done
+    if (tid == 0) load_view_params(vp, vw, view, a.H, a.W);
+    __syncthreads();
+    const int ticket = chunk * a.VV + view;
+
+    // ---- per-Gaussian projection -------------------------------------------------------------
+    Rec out;
+    out.q0 = make_float4(0.f, 0.f, -1e30f, -1e30f); out.q1 = make_float4(0.f, 0.f, 0.f, 0.f); out.q2 = out.q1; out.q3 = out.q1;
+    uint32_t tiles = 0;
+    int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
+    float depth = 0.f;
+    if (tid < n) {
+      const float m[3] = {__fmul_rn(mraw[0], vp.s), __fmul_rn(mraw[1], vp.s), __fmul_rn(mraw[2], vp.s)};
+      const float phx = xform_row(vp.proj, 0, m[0], m[1], m[2]);
+      const float phy = xform_row(vp.proj, 1, m[0], m[1], m[2]);
+      const float phw = xform_row(vp.proj, 3, m[0], m[1], m[2]);
+      const float pw = __frcp_rn(__fadd_rn(phw, 0.0000001f));
+      const float ppx = __fmul_rn(phx, pw), ppy = __fmul_rn(phy, pw);
+      const float pvz = xform_row(vp.view, 2, m[0], m[1], m[2]);
+      if (pvz > NEAR_CULL) {
+        float c6[6];
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-              float r = eval_sh_channel(sc.sh_degree, cs + ch * cstride, kstride, dx, dy, dz) + 0.5f;
-              if (r < 0.f) flags |= (1u << ch);
-              rgb[ch] = fmaxf(r, 0.f);
+        for (int k = 0; k < 6; k++) c6[k] = __fmul_rn(craw[k], vp.s2);
+        Cov2D q;
+        compute_cov2d(m, c6, vp, q);
+        const float det = __fsub_rn(__fmul_rn(q.a, q.c), __fmul_rn(q.b, q.b));
+        if (det != 0.0f) {
+          const float det_inv = __frcp_rn(det);
+          const float mid = __fmul_rn(0.5f, __fadd_rn(q.a, q.c));
+          const float disc = __fsqrt_rn(fmaxf(LAMBDA_FLOOR, __fsub_rn(__fmul_rn(mid, mid), det)));
+          const float lam = fmaxf(__fadd_rn(mid, disc), __fsub_rn(mid, disc));
+          const float radf = ceilf(__fmul_rn(3.f, __fsqrt_rn(lam)));
+          const int radius = (int)radf;
+          const float px = ndc2pix(ppx, a.W), py = ndc2pix(ppy, a.H);
+          get_rect(px, py, radius, a.grid_x, a.grid_y, rx0, ry0, rx1, ry1);
+          tiles = (uint32_t)((rx1 - rx0) * (ry1 - ry0));
+          if (tiles > 0) {
+            depth = pvz;
+            float rgb[3];
+            uint32_t flags = 0;
+            if (precomp) {
+              rgb[0] = cs[0]; rgb[1] = cs[1]; rgb[2] = cs[2];
+            } else {
+              float dx = m[0] - vp.campos[0], dy = m[1] - vp.campos[1], dz = m[2] - vp.campos[2];
+              const float len = __fsqrt_rn(dot3c(dx, dx, dy, dy, dz, dz));
+              dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
+#pragma unroll
+              for (int ch = 0; ch < 3; ch++) {
+                float r = eval_sh_channel(deg, cs + ch * cstride, kstride, dx, dy, dz) + 0.5f;
+                if (r < 0.f) flags |= (1u << ch);
+                rgb[ch] = fmaxf(r, 0.f);
+              }
             }
+            float zc = 0.f;
+            if (vw.depth_mode != B200S_DEPTH_NONE) {
+              const float z = __fadd_rn(__fmaf_rn(vp.daff[2], mraw[2], __fmaf_rn(vp.daff[0], mraw[0], __fmul_rn(vp.daff[1], mraw[1]))), vp.daff[3]);
+              if (vw.depth_mode == B200S_DEPTH_Z) zc = z;
+              else if (vw.depth_mode == B200S_DEPTH_DISPARITY) zc = __frcp_rn(z);
+              else zc = logf(fmaxf(fminf(z, vp.dnear), vp.dfar));
+            }
+            // conservative half-extents of the region where alpha can reach 1/255
+            float ex = -1e30f, ey = -1e30f;  // never reaches alpha >= 1/255: fails every sub-tile test
+            const float o255 = 255.0f * opac;
+            if (o255 >= 1.0f) {
+              const float tau2 = 2.0f * logf(o255);
+              ex = sqrtf(tau2 * q.a) * 1.01f + 0.1f;
+              ey = sqrtf(tau2 * q.c) * 1.01f + 0.1f;
+            }
+            out.q0 = make_float4(px, py, ex, ey);
+            out.q1 = make_float4(__fmul_rn(q.c, det_inv), __fmul_rn(-q.b, det_inv), __fmul_rn(q.a, det_inv), opac);
+            out.q2 = make_float4(rgb[0], rgb[1], rgb[2], zc);
+            const uint32_t rect = (uint32_t)rx0 | ((uint32_t)ry0 << 8) | ((uint32_t)rx1 << 16) | ((uint32_t)ry1 << 24);
+            out.q3 = make_float4(depth, __int_as_float(radius), __uint_as_float(rect), __uint_as_float(flags));
           }
-          float zc = 0.f;
-          if (vw.depth_mode != B200S_DEPTH_NONE) {
-            const float z = __fadd_rn(__fmaf_rn(vp.daff[2], mraw[2], __fmaf_rn(vp.daff[0], mraw[0], __fmul_rn(vp.daff[1], mraw[1]))), vp.daff[3]);
-            if (vw.depth_mode == B200S_DEPTH_Z) zc = z;
-            else if (vw.depth_mode == B200S_DEPTH_DISPARITY) zc = __frcp_rn(z);
-            else zc = logf(fmaxf(fminf(z, vp.dnear), vp.dfar));
-          }
-          // conservative half-extents of the region where alpha can reach 1/255
-          float ex = -1e30f, ey = -1e30f;  // never reaches alpha >= 1/255: fails every sub-tile test
-          const float o255 = 255.0f * opac;
-          if (o255 >= 1.0f) {
-            const float tau2 = 2.0f * logf(o255);
-            ex = sqrtf(tau2 * q.a) * 1.01f + 0.1f;
-            ey = sqrtf(tau2 * q.c) * 1.01f + 0.1f;
-          }
-          out.q0 = make_float4(px, py, ex, ey);
-          out.q1 = make_float4(__fmul_rn(q.c, det_inv), __fmul_rn(-q.b, det_inv), __fmul_rn(q.a, det_inv), opac);
-          out.q2 = make_float4(rgb[0], rgb[1], rgb[2], zc);
-          const uint32_t rect = (uint32_t)rx0 | ((uint32_t)ry0 << 8) | ((uint32_t)rx1 << 16) | ((uint32_t)ry1 << 24);
-          out.q3 = make_float4(depth, __int_as_float(radius), __uint_as_float(rect), __uint_as_float(flags));
         }
       }
+      if (a.radii) a.radii[(long long)view * a.N + i0 + tid] = tiles > 0 ? __float_as_int(out.q3.y) : 0;
     }
-    if (a.radii) a.radii[(long long)view * a.N + i0 + tid] = tiles > 0 ? __float_as_int(out.q3.y) : 0;
-  }
 
-  // ---- binning word, tile total of the CTA, records out ----------------------------------------------
-  {
-    const uint32_t rect = tiles ? ((uint32_t)rx0 | ((uint32_t)ry0 << 8) | ((uint32_t)rx1 << 16) | ((uint32_t)ry1 << 24)) : 0u;
-    a.bin_info[(size_t)ticket * PRE_THREADS + tid] = make_uint2(__float_as_uint(depth), rect);
-  }
-  uint32_t sum = tiles;
+    // ---- binning word, tile total of the (chunk, view), records out -------------------------------
+    {
+      const uint32_t rect = tiles ? ((uint32_t)rx0 | ((uint32_t)ry0 << 8) | ((uint32_t)rx1 << 16) | ((uint32_t)ry1 << 24)) : 0u;
+      a.bin_info[(size_t)ticket * PRE_THREADS + tid] = make_uint2(__float_as_uint(depth), rect);
+    }
+    uint32_t sum = tiles;
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-  if (lane == 0) s_warp_tot[warp] = sum;
-  const uint32_t vis_mask = __ballot_sync(0xffffffffu, tiles > 0);
-  if (lane == 0 && vis_mask) atomicAdd(&a.status->num_visible, (uint32_t)__popc(vis_mask));
-  __syncthreads();  // everyone is done reading the staged inputs; warp totals visible
-  if (tid == 0) {
-    uint32_t t = 0;
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) s_warp_tot[warp] = sum;
+    const uint32_t vis_mask = __ballot_sync(0xffffffffu, tiles > 0);
+    if (lane == 0 && vis_mask) atomicAdd(&a.status->num_visible, (uint32_t)__popc(vis_mask));
+    s_rec[tid * 4 + 0] = out.q0; s_rec[tid * 4 + 1] = out.q1; s_rec[tid * 4 + 2] = out.q2; s_rec[tid * 4 + 3] = out.q3;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t t = 0;
 #pragma unroll
-    for (int w = 0; w < PRE_THREADS / 32; w++) t += s_warp_tot[w];
-    a.ticket_totals[ticket] = t;
+      for (int w = 0; w < PRE_THREADS / 32; w++) t += s_warp_tot[w];
+      a.ticket_totals[ticket] = t;
+    }
+    float4* dst = reinterpret_cast<float4*>(a.rec + (long long)view * a.N + i0);
+    for (int i = tid; i < n * 4; i += PRE_THREADS) dst[i] = s_rec[i];
   }
-  float4* s_rec = reinterpret_cast<float4*>(smem);  // [256*4]
-  s_rec[tid * 4 + 0] = out.q0; s_rec[tid * 4 + 1] = out.q1; s_rec[tid * 4 + 2] = out.q2; s_rec[tid * 4 + 3] = out.q3;
-  __syncthreads();
-  float4* dst = reinterpret_cast<float4*>(a.rec + (long long)view * a.N + i0);
-  for (int i = tid; i < n * 4; i += PRE_THREADS) dst[i] = s_rec[i];
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -396,15 +412,19 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   const int scan_blocks = (plan.pre_tickets + SCAN_TILE - 1) / SCAN_TILE;
   if ((e = cudaMemsetAsync(a.scan_blocks, 0, (size_t)scan_blocks * sizeof(uint64_t), stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(a.hist, 0, 8 * 256 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
-  size_t smem = (size_t)PRE_THREADS * a.fpg * sizeof(float);
-  if (smem < (size_t)PRE_THREADS * sizeof(Rec)) smem = (size_t)PRE_THREADS * sizeof(Rec);
+  const size_t smem = (size_t)PRE_THREADS * a.fpg * sizeof(float) + (size_t)PRE_THREADS * sizeof(Rec);
+  const bool specialised = sc.cov_layout == B200S_COV_3X3 && !sc.colors_precomp && sc.sh_layout == B200S_SH_CHANNEL_MAJOR &&
+                           sc.sh_coeffs == 9 && sc.sh_degree == 2;
   static thread_local size_t configured = 0;
   if (smem > configured) {
-    if ((e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     configured = smem;
   }
   if (plan.pre_tickets > 0) {
-    project_kernel<<<plan.pre_tickets, PRE_THREADS, smem, stream>>>(sc, vw, a);
+    const int proj_blocks = a.chunks * sc.num_scenes;
+    if (specialised) project_kernel<true><<<proj_blocks, PRE_THREADS, smem, stream>>>(sc, vw, a);
+    else project_kernel<false><<<proj_blocks, PRE_THREADS, smem, stream>>>(sc, vw, a);
     scan_kernel<<<scan_blocks, SCAN_THREADS, 0, stream>>>(a);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
