@@ -82,7 +82,7 @@ typedef struct B200sViews {
 /* Problem dimensions -> workspace plan. */
 typedef struct B200sDims {
   int32_t num_scenes, num_gaussians, num_views, height, width;
-  int64_t pair_capacity; /* R_cap: capacity of the (key,value) pair buffers, < 2^32 */
+  int64_t pair_capacity; /* R_cap: capacity of the (key,value) pair buffers, < 2^32 - 8192 (list positions are 32-bit) */
 } B200sDims;
 
 /* Byte offsets of every region inside the two caller-owned workspaces.
@@ -112,7 +112,7 @@ typedef struct B200sPlan {
   size_t off_scan_blocks;        /* [pre_tickets / 2048 + 1] u64 decoupled look-back words of the scan */
   size_t off_bin_info;           /* [pre_tickets * 256] uint2 (depth bits, packed rect) per Gaussian-view */
   size_t off_hist;               /* [8,256] u32 digit histograms -> exclusive bases */
-  size_t off_lookback;           /* [2, sort_tiles_cap, 256] u32 onesweep look-back words */
+  size_t off_lookback;           /* [2, sort_tiles_cap, 256] u64 onesweep look-back words */
   size_t off_counters;           /* [64] u32 ticket / tile counters */
   size_t off_grad_rec;           /* backward only: [VV,N] 48-byte gradient records (may alias keys) */
 } B200sPlan;

@@ -101,8 +101,8 @@ int b200s_plan(const B200sDims* d, B200sPlan* p) {
   p->sort_bits = 32 + p->tile_bits + p->view_bits;
   p->sort_passes = (p->sort_bits + 7) / 8;
   if (p->sort_passes > 8) return B200S_EBADARG;
-  // the onesweep look-back word holds a 30-bit running count
-  if (d->pair_capacity >= (1ll << 30)) return B200S_EBADARG;
+  // list positions (tile ranges, sort scatter) are 32-bit
+  if (d->pair_capacity >= (1ll << 32) - 8192) return B200S_EBADARG;
   const long long chunks = (d->num_gaussians + PRE_THREADS - 1) / PRE_THREADS;
   if (chunks * d->num_views > 0x7fffffffll) return B200S_EBADARG;
   p->pre_tickets = (int)(chunks * d->num_views);
@@ -129,7 +129,7 @@ int b200s_plan(const B200sDims* d, B200sPlan* p) {
   p->off_scan_blocks = o; o = align_up(o + ((size_t)p->pre_tickets / 2048 + 2) * 8);
   p->off_bin_info = o; o = align_up(o + (size_t)p->pre_tickets * PRE_THREADS * 8);
   p->off_hist = o; o = align_up(o + 8 * 256 * 4);
-  p->off_lookback = o; o = align_up(o + 2 * (size_t)p->sort_tiles_cap * 256 * 4);
+  p->off_lookback = o; o = align_up(o + 2 * (size_t)p->sort_tiles_cap * 256 * 8);
   p->off_counters = o; o = align_up(o + CNT_WORDS * 4);
   const size_t fwd_bytes = o;
   p->off_grad_rec = 0;  // backward reuses the scratch from its start (keys are dead by then)
@@ -180,7 +180,7 @@ int b200s_forward_render(const B200sScene* sc, const B200sViews* vw, const B200s
   uint32_t* vals_a = reinterpret_cast<uint32_t*>(saved + pl->off_vals_a);
   uint32_t* vals_b = reinterpret_cast<uint32_t*>(scratch + pl->off_vals_b);
   cudaError_t e = launch_sort(keys_a, vals_a, keys_b, vals_b, pl->sort_passes, pl->pair_capacity, cnt, reinterpret_cast<uint32_t*>(scratch + pl->off_hist),
-                              reinterpret_cast<uint32_t*>(scratch + pl->off_lookback), reinterpret_cast<uint32_t*>(scratch + pl->off_counters), sm_count(), stream,
+                              reinterpret_cast<uint64_t*>(scratch + pl->off_lookback), reinterpret_cast<uint32_t*>(scratch + pl->off_counters), sm_count(), stream,
                               /*hist_ready=*/true);
   if (e != cudaSuccess) return fail(e);
   uint2* ranges = reinterpret_cast<uint2*>(saved + pl->off_ranges);
@@ -235,12 +235,12 @@ int b200s_backward(const B200sScene* sc, const B200sViews* vw, const B200sPlan* 
 size_t b200s_sort_tmp_bytes(int64_t n) { return sort_tmp_bytes(n); }
 
 int b200s_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, int32_t bits, void* tmp, void* stream) {
-  if (!keys_a || !vals_a || !keys_b || !vals_b || !tmp || n < 0 || bits <= 0 || bits > 64 || n >= (1ll << 30)) return B200S_EBADARG;
+  if (!keys_a || !vals_a || !keys_b || !vals_b || !tmp || n < 0 || bits <= 0 || bits > 64 || n >= (1ll << 32) - 8192) return B200S_EBADARG;
   if (n == 0) return B200S_OK;
   const int passes = (bits + 7) / 8;
   uint32_t* hist = reinterpret_cast<uint32_t*>(tmp);
-  uint32_t* lookback = hist + 8 * 256;
-  uint32_t* counters = lookback + 2 * (size_t)sort_tiles_for(n) * 256;
+  uint64_t* lookback = reinterpret_cast<uint64_t*>(hist + 8 * 256);
+  uint32_t* counters = reinterpret_cast<uint32_t*>(lookback + 2 * (size_t)sort_tiles_for(n) * 256);
   // the stand-alone entry point takes its input in A: an odd pass count needs it in B first
   cudaStream_t s = (cudaStream_t)stream;
   if (passes % 2) {

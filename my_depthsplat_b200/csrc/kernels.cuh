@@ -40,7 +40,7 @@ cudaError_t launch_preprocess_bin(const B200sScene&, const B200sViews&, const B2
 size_t sort_tmp_bytes(long long n_cap);
 int sort_tiles_for(long long n_cap);
 cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int passes, long long n_cap, CountRef cnt,
-                        uint32_t* hist, uint32_t* lookback, uint32_t* counters, int sm_count, cudaStream_t, bool hist_ready);
+                        uint32_t* hist, uint64_t* lookback, uint32_t* counters, int sm_count, cudaStream_t, bool hist_ready);
 cudaError_t launch_tile_ranges(const uint64_t* keys, CountRef cnt, uint2* ranges, int bins, long long n_cap, int sm_count, cudaStream_t);
 cudaError_t launch_composite_fwd(const CompArgs&, int tiles, int views, bool depth, bool count, cudaStream_t);
 cudaError_t launch_composite_bwd(const CompArgs&, int tiles, int views, bool depth, cudaStream_t);

@@ -21,7 +21,8 @@ constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per tile
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX = 256;
-constexpr uint32_t LB_FLAG_AGG = 1u << 30, LB_FLAG_PREFIX = 2u << 30, LB_VALUE_MASK = (1u << 30) - 1;
+// look-back words are 64-bit (2 flag bits + count) so that one call can sort up to 2^32 - 1 pairs
+constexpr uint64_t LB_FLAG_AGG = 1ull << 62, LB_FLAG_PREFIX = 2ull << 62, LB_VALUE_MASK = (1ull << 62) - 1;
 
 __device__ __forceinline__ unsigned long long resolve_count(const CountRef& c) {
   if (c.overflow_dev && *c.overflow_dev) return 0ull;
@@ -115,8 +116,8 @@ struct PassArgs {
   const uint64_t* keys_in; const uint32_t* vals_in;
   uint64_t* keys_out; uint32_t* vals_out;
   const uint32_t* gbase;   // [256] exclusive digit bases of this pass
-  uint32_t* lb_cur;        // [tiles][256] look-back words of this pass (zeroed)
-  uint32_t* lb_next;       // same for the next pass: this pass zeroes the rows it owns
+  uint64_t* lb_cur;        // [tiles][256] look-back words of this pass (zeroed)
+  uint64_t* lb_next;       // same for the next pass: this pass zeroes the rows it owns
   uint32_t* tile_counter;  // dynamic tile id
   CountRef cnt;
   int shift;
@@ -243,32 +244,32 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const Pa
   }
   uint32_t prev = 0;
   {
-    uint32_t* row = a.lb_cur + (size_t)tile * RADIX + tid;
+    uint64_t* row = a.lb_cur + (size_t)tile * RADIX + tid;
     if (tile == 0) {
-      st_volatile_u32(row, LB_FLAG_PREFIX | run);
+      st_volatile_u64(row, LB_FLAG_PREFIX | run);
     } else {
-      st_volatile_u32(row, LB_FLAG_AGG | run);
+      st_volatile_u64(row, LB_FLAG_AGG | run);
       // decoupled look-back, LOOKBACK_BATCH predecessors per round trip
       int t = (int)tile - 1;
       bool found = false;
       while (!found) {
-        uint32_t w[LOOKBACK_BATCH];
+        uint64_t w[LOOKBACK_BATCH];
 #pragma unroll
         for (int k = 0; k < LOOKBACK_BATCH; k++)
-          w[k] = (t - k >= 0) ? ld_volatile_u32(a.lb_cur + (size_t)(t - k) * RADIX + tid) : LB_FLAG_PREFIX;
+          w[k] = (t - k >= 0) ? ld_volatile_u64(a.lb_cur + (size_t)(t - k) * RADIX + tid) : LB_FLAG_PREFIX;
         int adv = 0;
 #pragma unroll
         for (int k = 0; k < LOOKBACK_BATCH; k++) {
-          const uint32_t f = w[k] >> 30;
+          const uint32_t f = (uint32_t)(w[k] >> 62);
           if (!found && adv == k && f != 0) {
-            prev += w[k] & LB_VALUE_MASK;
+            prev += (uint32_t)(w[k] & LB_VALUE_MASK);  // positions are taken modulo 2^32 (< 2^32 pairs per call)
             adv = k + 1;
             if (f == 2) found = true;
           }
         }
         t -= adv;
       }
-      st_volatile_u32(row, LB_FLAG_PREFIX | (prev + run));
+      st_volatile_u64(row, LB_FLAG_PREFIX | (uint64_t)(uint32_t)(prev + run));
     }
   }
   // ---- exclusive scan over digits of the tile counts -> start of each digit inside the tile
@@ -331,20 +332,20 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __rest
 // host side
 size_t sort_tmp_bytes(long long n_cap) {
   const size_t tiles = (size_t)((n_cap + SORT_TILE - 1) / SORT_TILE) + 1;
-  return 8 * RADIX * sizeof(uint32_t) + 2 * tiles * RADIX * sizeof(uint32_t) + CNT_WORDS * sizeof(uint32_t);
+  return 8 * RADIX * sizeof(uint32_t) + 2 * tiles * RADIX * sizeof(uint64_t) + CNT_WORDS * sizeof(uint32_t);
 }
 int sort_tiles_for(long long n_cap) { return (int)((n_cap + SORT_TILE - 1) / SORT_TILE) + 1; }
 
 // Sorts on the low `passes*8` bits.  Input in (keys_in, vals_in) = A if passes is even, else B;
 // the output always ends in the A buffers.  hist [8*256], lookback [2*tiles*256], counters [CNT_WORDS].
 cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int passes, long long n_cap,
-                        CountRef cnt, uint32_t* hist, uint32_t* lookback, uint32_t* counters, int sm_count, cudaStream_t stream,
+                        CountRef cnt, uint32_t* hist, uint64_t* lookback, uint32_t* counters, int sm_count, cudaStream_t stream,
                         bool hist_ready) {
   if (passes <= 0 || n_cap <= 0) return cudaSuccess;
   cudaError_t e;
   const int tiles = sort_tiles_for(n_cap);
   if (!hist_ready && (e = cudaMemsetAsync(hist, 0, 8 * RADIX * sizeof(uint32_t), stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(lookback, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(lookback, 0, (size_t)tiles * RADIX * sizeof(uint64_t), stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(counters + CNT_SORT_TILE0, 0, 8 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   const bool start_in_a = (passes % 2) == 0;
   uint64_t* kin = start_in_a ? keys_a : keys_b; uint32_t* vin = start_in_a ? vals_a : vals_b;

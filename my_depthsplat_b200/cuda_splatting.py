@@ -96,7 +96,7 @@ def render_views(
     except PairLimitExceeded:
         if V == 1:
             raise
-    # more than 2^30 (tile, Gaussian) pairs in one call (huge Gaussians, many views): split the views and
+    # more than 2^32 (tile, Gaussian) pairs in one call (huge Gaussians, many views): split the views and
     # concatenate -- each half is its own autograd node, gradients add up as usual
     half = V // 2
     bgs = (background_color, background_color) if background_color.dim() == 1 else (background_color[:, :half], background_color[:, half:])

@@ -59,8 +59,11 @@ debug_keep = False
 debug_last: Optional[dict] = None
 
 
+_PAIR_LIMIT = (1 << 32) - 8193  # list positions are 32-bit
+
+
 class PairLimitExceeded(RuntimeError):
-    """One call would produce more than 2^30 (tile, Gaussian) pairs; render fewer views per call."""
+    """One call would produce 2^32 or more (tile, Gaussian) pairs; render fewer views per call."""
 
 
 class _HostStatusRing:
@@ -193,7 +196,7 @@ class _Rasterize(torch.autograd.Function):
 
         key = (dev.index, B, N, VV, H, W)
         cap = _capacity_hint.get(key) or max(4 * N * VV, 1 << 16)
-        cap = min(cap, (1 << 30) - 1)
+        cap = min(cap, _PAIR_LIMIT)
         words = _status_ring.words
         retries = 0
         import time as _t
@@ -226,11 +229,11 @@ class _Rasterize(torch.autograd.Function):
                 break
             words[2 * slot] = 0
             words[2 * slot + 1] = 0
-            if num_pairs >= (1 << 30) - 1:
-                raise PairLimitExceeded(f"{num_pairs} (tile, Gaussian) pairs in one call exceed the 2^30 limit; render fewer views per call")
-            cap = min(int(num_pairs * 1.25) + 4096, (1 << 30) - 1)
+            if num_pairs >= _PAIR_LIMIT:
+                raise PairLimitExceeded(f"{num_pairs} (tile, Gaussian) pairs in one call exceed the 2^32 limit; render fewer views per call")
+            cap = min(int(num_pairs * 1.25) + 4096, _PAIR_LIMIT)
             retries += 1
-        _capacity_hint[key] = min(max(int(num_pairs * 1.25) + 4096, 1 << 16), (1 << 30) - 1)
+        _capacity_hint[key] = min(max(int(num_pairs * 1.25) + 4096, 1 << 16), _PAIR_LIMIT)
 
         st = last_stats
         st.num_pairs, st.pair_capacity, st.retries = num_pairs, cap, retries

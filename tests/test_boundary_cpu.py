@@ -72,7 +72,7 @@ def test_plan_rejects_bad_arguments():
     with pytest.raises(ValueError):
         _lib.plan(1, 100, 1, 16, 16, 0)
     with pytest.raises(ValueError):
-        _lib.plan(1, 100, 1, 16, 16, 1 << 31)       # look-back words hold 30-bit counts
+        _lib.plan(1, 100, 1, 16, 16, 1 << 32)       # list positions are 32-bit
     with pytest.raises(ValueError):
         _lib.plan(1, 100, 1, 16 * 300, 16, 1024)     # rect packing: at most 255 tiles per axis
 
