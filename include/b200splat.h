@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 3
+#define B200S_ABI_VERSION 4
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -150,6 +150,11 @@ typedef struct B200sGradIn { /* all fp32, OVERWRITTEN (summed over the views of 
   float* dL_dcolors;      /* [B,N,3] when colors_precomp was used, or NULL */
   float* dL_dopacities;   /* [B,N] */
   float* dL_dmeans2D;     /* [VV,N,3] screen-space mean gradients (extension API parity), or NULL */
+  int32_t multicast;      /* != 0: dL_dmeans / dL_dcovariances / dL_dharmonics|dL_dcolors / dL_dopacities are NVLS MULTICAST
+                             addresses of zero-initialised symmetric buffers (one replica per GPU of the process group): the
+                             kernel ADDS its result with multimem.red, so that after a barrier every GPU holds the sum over
+                             all ranks -- the preprocess backward and the gradient all-reduce of view-sharded training are one
+                             pass, the reduction happens in the NVSwitch. */
 } B200sGradIn;
 
 /* Pure host function: fills the plan for the given dimensions.  No CUDA calls. */

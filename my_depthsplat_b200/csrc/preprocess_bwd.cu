@@ -32,13 +32,31 @@ __device__ __forceinline__ void stage_in_bwd(float* dst, const float* __restrict
     for (int i = threadIdx.x; i < count; i += PRE_THREADS) { const int g = i / k; dst[g * stride + (i - g * k)] = __ldg(src + i); }
   }
 }
+// NVLS: add to every replica the multicast address maps to (the switch performs the reduction)
+__device__ __forceinline__ void multimem_red_add_v4(float* mc_addr, const float4 v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_red_add(float* mc_addr, const float v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
+
+// shared -> global, coalesced; MC = the destination is a multicast address and the values are ADDED (multimem.red)
+template <bool MC>
 __device__ __forceinline__ void stage_out_bwd(float* __restrict__ dst, const float* src, int count, int k, int stride) {
   if (k == stride && (((uintptr_t)dst) & 15) == 0 && (count & 3) == 0) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = threadIdx.x; i < (count >> 2); i += PRE_THREADS) d4[i] = s4[i];
+    for (int i = threadIdx.x; i < (count >> 2); i += PRE_THREADS) {
+      if (MC) multimem_red_add_v4(reinterpret_cast<float*>(d4 + i), s4[i]);
+      else d4[i] = s4[i];
+    }
   } else {
-    for (int i = threadIdx.x; i < count; i += PRE_THREADS) { const int g = i / k; dst[i] = src[g * stride + (i - g * k)]; }
+    for (int i = threadIdx.x; i < count; i += PRE_THREADS) {
+      const int g = i / k;
+      const float v = src[g * stride + (i - g * k)];
+      if (MC) multimem_red_add(dst + i, v);
+      else dst[i] = v;
+    }
   }
 }
 
@@ -51,7 +69,7 @@ __device__ __forceinline__ void dnormvdv(const float v[3], const float dv[3], fl
 }
 
 // NC = SH coefficients per channel that are ACTIVE ((deg+1)^2); NC == 0 -> colors_precomp path.
-template <int NC>
+template <int NC, bool MC>
 __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B200sScene sc, const B200sViews vw, const B200sGradIn gin,
                                                                      const PreBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -257,11 +275,15 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
     }
   }
   __syncthreads();
-  stage_out_bwd(gin.dL_dmeans + g0 * 3, s_dmean, n * 3, 3, 3);
-  stage_out_bwd(gin.dL_dcovariances + g0 * a.cov_floats, s_dcov, n * a.cov_floats, a.cov_floats, a.cov_floats);
+  stage_out_bwd<MC>(gin.dL_dmeans + g0 * 3, s_dmean, n * 3, 3, 3);
+  stage_out_bwd<MC>(gin.dL_dcovariances + g0 * a.cov_floats, s_dcov, n * a.cov_floats, a.cov_floats, a.cov_floats);
   float* col_dst = NC == 0 ? gin.dL_dcolors : gin.dL_dharmonics;
-  if (col_dst) stage_out_bwd(col_dst + g0 * a.col_floats, s_dcol, n * a.col_floats, a.col_floats, a.col_stride);
-  if (tid < n) gin.dL_dopacities[g0 + tid] = dop;
+  if (col_dst) stage_out_bwd<MC>(col_dst + g0 * a.col_floats, s_dcol, n * a.col_floats, a.col_floats, a.col_stride);
+  if (tid < n) {
+    if (MC) multimem_red_add(gin.dL_dopacities + g0 + tid, dop);
+    else gin.dL_dopacities[g0 + tid] = dop;
+  }
+  if (MC) __threadfence_system();  // the reductions are performed at the peers before the kernel is seen as complete
 }
 
 cudaError_t launch_preprocess_bwd(const B200sScene& sc, const B200sViews& vw, const B200sPlan& plan, const char* saved, char* scratch,
@@ -285,9 +307,15 @@ cudaError_t launch_preprocess_bwd(const B200sScene& sc, const B200sViews& vw, co
   count_launches(1);
 #define LAUNCH(NCV)                                                                                                        \
   {                                                                                                                        \
-    e = cudaFuncSetAttribute(preprocess_bwd_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-    if (e != cudaSuccess) return e;                                                                                        \
-    preprocess_bwd_kernel<NCV><<<blocks, PRE_THREADS, smem, stream>>>(sc, vw, gin, a);                                    \
+    if (gin.multicast) {                                                                                                   \
+      e = cudaFuncSetAttribute(preprocess_bwd_kernel<NCV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return e;                                                                                      \
+      preprocess_bwd_kernel<NCV, true><<<blocks, PRE_THREADS, smem, stream>>>(sc, vw, gin, a);                            \
+    } else {                                                                                                               \
+      e = cudaFuncSetAttribute(preprocess_bwd_kernel<NCV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);\
+      if (e != cudaSuccess) return e;                                                                                      \
+      preprocess_bwd_kernel<NCV, false><<<blocks, PRE_THREADS, smem, stream>>>(sc, vw, gin, a);                           \
+    }                                                                                                                      \
   }
   switch (nc) {
     case 0: LAUNCH(0); break;

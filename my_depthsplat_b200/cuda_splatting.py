@@ -83,6 +83,7 @@ def render_views(
     depth_mode: Optional[DepthRenderingMode] = None,
     want_radii: bool = False,
     count_work: bool = False,
+    grad_reducer=None,
 ):
     """All V views of all B scenes in one rasterizer call.  Returns (color [B,V,3,H,W],
     depth [B,V,H,W] | None) (+ radii [B,V,N] when want_radii)."""
@@ -92,7 +93,7 @@ def render_views(
     try:
         return _render_views_once(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
                                   gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh,
-                                  depth_mode, want_radii, count_work)
+                                  depth_mode, want_radii, count_work, grad_reducer)
     except PairLimitExceeded:
         if V == 1:
             raise
@@ -102,7 +103,7 @@ def render_views(
     bgs = (background_color, background_color) if background_color.dim() == 1 else (background_color[:, :half], background_color[:, half:])
     parts = [render_views(extrinsics[:, sl], intrinsics[:, sl], near[:, sl], far[:, sl], image_shape, bg, gaussian_means,
                           gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode,
-                          want_radii, count_work) for sl, bg in zip((slice(0, half), slice(half, V)), bgs)]
+                          want_radii, count_work, None) for sl, bg in zip((slice(0, half), slice(half, V)), bgs)]
     out = [torch.cat([p[0] for p in parts], dim=1),
            None if parts[0][1] is None else torch.cat([p[1] for p in parts], dim=1)]
     if want_radii:
@@ -111,7 +112,8 @@ def render_views(
 
 
 def _render_views_once(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means, gaussian_covariances,
-                       gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode, want_radii, count_work):
+                       gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode, want_radii, count_work,
+                       grad_reducer=None):
     B, V = extrinsics.shape[:2]
     h, w = image_shape
     dev = gaussian_means.device
@@ -140,7 +142,8 @@ def _render_views_once(extrinsics, intrinsics, near, far, image_shape, backgroun
     bg = bg.expand(B, V, 3).reshape(B * V, 3).contiguous() if bg.dim() == 1 else bg.reshape(B * V, 3).contiguous()
     scene_index = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(V)
 
-    pack = ViewPack(scene_index, view, full, campos, tanfov, bg, h, w, scale_pack, depth_mode, depth_affine, depth_clamp)
+    pack = ViewPack(scene_index, view, full, campos, tanfov, bg, h, w, scale_pack, depth_mode, depth_affine, depth_clamp,
+                    grad_reducer)
     if use_sh:
         degree = isqrt(gaussian_sh_coefficients.shape[-1]) - 1
         colors = gaussian_sh_coefficients

@@ -44,6 +44,7 @@ class Decoder(nn.Module, ABC, Generic[T]):
 
 class DecoderSplattingCUDA(Decoder[DecoderSplattingCUDACfg]):
     background_color: Tensor  # [3]
+    grad_reducer = None  # set by dist.ViewShardedDecoder(fused_reduce=True): cross-rank gradient sum inside the backward kernel
 
     def __init__(self, cfg: DecoderSplattingCUDACfg, dataset_cfg: Any) -> None:
         super().__init__(cfg, dataset_cfg)
@@ -55,7 +56,8 @@ class DecoderSplattingCUDA(Decoder[DecoderSplattingCUDACfg]):
         """gaussians [B,N,...]; extrinsics [B,V,4,4]; intrinsics [B,V,3,3]; near/far [B,V] ->
         DecoderOutput(color [B,V,3,H,W], depth [B,V,H,W] | None)."""
         color, depth = render_views(extrinsics, intrinsics, near, far, image_shape, self.background_color, gaussians.means,
-                                    gaussians.covariances, gaussians.harmonics, gaussians.opacities, depth_mode=depth_mode)
+                                    gaussians.covariances, gaussians.harmonics, gaussians.opacities, depth_mode=depth_mode,
+                                    grad_reducer=self.grad_reducer)
         return DecoderOutput(color, depth)
 
     def render_depth(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,

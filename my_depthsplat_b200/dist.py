@@ -89,17 +89,75 @@ def all_gather_views(local: Tensor, num_views: int, dim: int = 1, group: Optiona
     return torch.cat([b_.narrow(dim, 0, hi - lo) for b_, (lo, hi) in zip(bufs, sizes)], dim=dim)
 
 
+class FusedGradReducer:
+    """Sum of the per-Gaussian gradients over the ranks WITHOUT a separate collective: the preprocess-backward
+    kernel adds its results straight into NVLS multicast memory (``multimem.red``: the NVSwitch applies every
+    rank's contribution to every rank's replica), so the all-reduce of view-sharded training overlaps the
+    kernel that produces the data instead of following it.  Symmetric buffers come from
+    ``torch.distributed._symmetric_memory``; two of them alternate so that the consumer of step i may still
+    be reading while step i+1 accumulates.  Falls back (``available == False``) when the group has one rank
+    or the fabric offers no multicast."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        self._bufs = {}     # total floats -> [(tensor, handle)] * 2
+        self._turn = 0
+        self.available = self.world > 1 and torch.cuda.is_available()
+
+    def _get(self, nfloats: int, device):
+        key = (nfloats, device)
+        if key not in self._bufs:
+            import torch.distributed._symmetric_memory as symm_mem
+            pair = []
+            for _ in range(2):
+                t = symm_mem.empty(nfloats, dtype=torch.float32, device=device)
+                h = symm_mem.rendezvous(t, self.group)
+                if not h.multicast_ptr:
+                    self.available = False
+                    raise RuntimeError("no NVLS multicast on this fabric")
+                pair.append((t, h))
+            self._bufs[key] = pair
+        self._turn ^= 1
+        return self._bufs[key][self._turn]
+
+    def begin(self, shapes, device):
+        """-> (local gradient tensors, multicast addresses).  Zeroes this rank's replica and waits (on the
+        stream) until every rank has done so."""
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        offs, o = [], 0
+        for n in sizes:
+            offs.append(o)
+            o += (n + 3) // 4 * 4  # keep every segment 16-byte aligned for multimem.red.v4
+        buf, h = self._get(o, device)
+        buf.zero_()
+        h.barrier(channel=0)
+        self._cur = h
+        locals_ = [buf[a:a + n].view(s) for a, n, s in zip(offs, sizes, shapes)]
+        return locals_, [h.multicast_ptr + 4 * a for a in offs]
+
+    def end(self):
+        """All ranks' contributions have landed once this barrier has passed on the stream."""
+        self._cur.barrier(channel=1)
+
+
 class ViewShardedDecoder(torch.nn.Module):
     """Wraps a decoder (``DecoderSplattingCUDA`` or anything with its ``forward`` signature): every rank
     renders its contiguous slice of the target views of every scene; per-Gaussian gradients are summed
     across ranks in the backward.  ``gather=True`` returns the full ``[B, V, ...]`` frames on every rank
     (inference); otherwise the local slice (training: the loss is computed on the local views)."""
 
-    def __init__(self, decoder: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, gather: bool = False):
+    def __init__(self, decoder: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, gather: bool = False,
+                 fused_reduce: bool = False):
         super().__init__()
         self.decoder = decoder
         self.group = group
         self.gather = gather
+        # fused_reduce: the backward kernel reduces across ranks itself (NVLS multimem), no all-reduce afterwards
+        self.reducer = None
+        if fused_reduce and dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(decoder, "grad_reducer"):
+            self.reducer = FusedGradReducer(group)
+            decoder.grad_reducer = self.reducer
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
                 image_shape: tuple[int, int], depth_mode=None) -> DecoderOutput:
@@ -107,7 +165,8 @@ class ViewShardedDecoder(torch.nn.Module):
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         V = extrinsics.shape[1]
         sl = [shard_views(t, world, rank) for t in (extrinsics, intrinsics, near, far)]
-        g = sync_gaussian_grads(gaussians, self.group) if torch.is_grad_enabled() else gaussians
+        fused = self.reducer is not None and self.reducer.available
+        g = sync_gaussian_grads(gaussians, self.group) if (torch.is_grad_enabled() and not fused) else gaussians
         out = self.decoder.forward(g, *sl, image_shape, depth_mode=depth_mode)
         if self.gather and world > 1:
             color = all_gather_views(out.color, V, group=self.group)

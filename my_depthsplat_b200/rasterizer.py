@@ -38,6 +38,7 @@ class ViewPack:
     depth_mode: Optional[str] = None
     depth_affine: Optional[torch.Tensor] = None  # [VV,4]
     depth_clamp: Optional[torch.Tensor] = None   # [VV,2]
+    grad_reducer: Optional[object] = None        # dist.FusedGradReducer: sum the gradients over ranks inside the kernel
 
 
 @dataclass
@@ -276,18 +277,26 @@ class _Rasterize(torch.autograd.Function):
                        else g_depth.to(torch.float32).contiguous())
         else:
             g_depth = None
-        d_means = torch.empty_like(means)
-        d_covs = torch.empty_like(covs)
-        d_colors = torch.empty_like(colors)
-        d_op = torch.empty_like(opacities)
         d_m2d = torch.empty((VV, N, 3), dtype=torch.float32, device=dev) if want_m2d else None
         scratch = _scratch(dev, plan.scratch_bytes)
         gout = _lib.GradOut(_ptr(g_color), _ptr(g_depth))
-        gin = _lib.GradIn(_ptr(d_means), _ptr(d_covs), _ptr(d_colors) if use_sh else None, None if use_sh else _ptr(d_colors),
-                          _ptr(d_op), _ptr(d_m2d))
+        reducer = vp.grad_reducer if (vp.grad_reducer is not None and getattr(vp.grad_reducer, "available", False)) else None
+        if reducer is not None:
+            # outputs are NVLS multicast addresses: the kernel ADDS into every rank's (zeroed) replica
+            (d_means, d_covs, d_colors, d_op), mc = reducer.begin([means.shape, covs.shape, colors.shape, opacities.shape], dev)
+            gin = _lib.GradIn(mc[0], mc[1], mc[2] if use_sh else None, None if use_sh else mc[2], mc[3], _ptr(d_m2d), 1)
+        else:
+            d_means = torch.empty_like(means)
+            d_covs = torch.empty_like(covs)
+            d_colors = torch.empty_like(colors)
+            d_op = torch.empty_like(opacities)
+            gin = _lib.GradIn(_ptr(d_means), _ptr(d_covs), _ptr(d_colors) if use_sh else None, None if use_sh else _ptr(d_colors),
+                              _ptr(d_op), _ptr(d_m2d), 0)
         out = _lib.Out(None, None, None, 0)
         _lib.check(L.b200s_backward(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(), C.byref(out),
                                     C.byref(gout), C.byref(gin), stream), "b200s_backward")
+        if reducer is not None:
+            reducer.end()
         return d_means, d_covs, d_colors, d_op, d_m2d, None, None, None, None, None, None
 
 
