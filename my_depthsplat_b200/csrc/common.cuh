@@ -184,6 +184,36 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---- TMA (bulk async copy engine) staging of contiguous global ranges into shared memory ---------
+// One thread arms an mbarrier with the byte count and issues cp.async.bulk (SASS: UBLKCP); the copy
+// engine moves the data while the CTA's threads do nothing, and everyone waits on the barrier's phase.
+// Requirements: 16-byte aligned source, destination and size.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+      "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ bool tma_ok(const void* src, int bytes) { return ((((uintptr_t)src) | (uintptr_t)bytes) & 15) == 0 && bytes > 0; }
+
 // counters block layout (u32 indices)
 constexpr int CNT_PRE_TICKET = 0;
 constexpr int CNT_SORT_TILE0 = 8;  // + pass (8 passes)

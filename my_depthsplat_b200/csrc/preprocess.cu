@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
   extern __shared__ __align__(16) float smem[];
   __shared__ ViewParams vp;
   __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
+  __shared__ __align__(8) uint64_t s_bar;
 
   const int cov_floats = SPECIALISED ? 9 : a.cov_floats;
   const int col_floats = SPECIALISED ? 27 : a.col_floats;
@@ -116,12 +117,33 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
   float* s_op = s_cov + PRE_THREADS * cov_floats;        // [256]
   float* s_col = s_op + PRE_THREADS;                     // [256*col_stride]
   float4* s_rec = reinterpret_cast<float4*>(s_col + PRE_THREADS * col_stride);  // [256*4] record staging
-  stage_in(s_mean, sc.means + g0 * 3, n * 3);
-  stage_in(s_cov, sc.covariances + g0 * cov_floats, n * cov_floats);
-  stage_in(s_op, sc.opacities + g0, n);
   const float* col_src = precomp ? sc.colors_precomp : sc.harmonics;
-  stage_in_padded(s_col, col_src + g0 * col_floats, n * col_floats, col_floats, col_stride);
-  __syncthreads();
+  {
+    const float* g_mean = sc.means + g0 * 3; const float* g_cov = sc.covariances + g0 * cov_floats;
+    const float* g_op = sc.opacities + g0; const float* g_col = col_src + g0 * col_floats;
+    // contiguous ranges with 16-byte aligned ends go through the TMA bulk copy engine (four copies, one barrier);
+    // ragged / misaligned chunks and padded colour rows fall back to cooperative loads
+    const bool tma = col_floats == col_stride && tma_ok(g_mean, n * 12) && tma_ok(g_cov, n * cov_floats * 4) && tma_ok(g_op, n * 4) &&
+                     tma_ok(g_col, n * col_floats * 4);
+    if (tma) {
+      if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_expect_tx(&s_bar, (uint32_t)(n * 4 * (3 + cov_floats + 1 + col_floats)));
+        tma_bulk_load(s_mean, g_mean, n * 12, &s_bar);
+        tma_bulk_load(s_cov, g_cov, n * cov_floats * 4, &s_bar);
+        tma_bulk_load(s_op, g_op, n * 4, &s_bar);
+        tma_bulk_load(s_col, g_col, n * col_floats * 4, &s_bar);
+      }
+      __syncthreads();  // the barrier is initialised before anyone waits on it
+      mbar_wait(&s_bar, 0);
+    } else {
+      stage_in(s_mean, g_mean, n * 3);
+      stage_in(s_cov, g_cov, n * cov_floats);
+      stage_in(s_op, g_op, n);
+      stage_in_padded(s_col, g_col, n * col_floats, col_floats, col_stride);
+      __syncthreads();
+    }
+  }
   float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, opac = 0.f;
   if (tid < n) {
     mraw[0] = s_mean[tid * 3]; mraw[1] = s_mean[tid * 3 + 1]; mraw[2] = s_mean[tid * 3 + 2];

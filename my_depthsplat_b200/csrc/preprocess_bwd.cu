@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
                                                                      const PreBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ ViewParams vp;
+  __shared__ __align__(8) uint64_t s_bar;
   if (*a.overflow) return;
   constexpr int DEG = NC == 16 ? 3 : (NC == 9 ? 2 : (NC == 4 ? 1 : 0));
   constexpr int NACC = NC > 0 ? 3 * NC : 3;
@@ -87,10 +88,28 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
   float* s_mean = smem;
   float* s_cov = s_mean + PRE_THREADS * 3;
   float* s_col = s_cov + PRE_THREADS * a.cov_floats;
-  stage_in_bwd(s_mean, sc.means + g0 * 3, n * 3, 3, 3);
-  stage_in_bwd(s_cov, sc.covariances + g0 * a.cov_floats, n * a.cov_floats, a.cov_floats, a.cov_floats);
-  if (NC > 0) stage_in_bwd(s_col, sc.harmonics + g0 * a.col_floats, n * a.col_floats, a.col_floats, a.col_stride);
-  __syncthreads();
+  {
+    const float* g_mean = sc.means + g0 * 3; const float* g_cov = sc.covariances + g0 * a.cov_floats;
+    const float* g_col = NC > 0 ? sc.harmonics + g0 * a.col_floats : nullptr;
+    const bool tma = a.col_floats == a.col_stride && tma_ok(g_mean, n * 12) && tma_ok(g_cov, n * a.cov_floats * 4) &&
+                     (NC == 0 || tma_ok(g_col, n * a.col_floats * 4));
+    if (tma) {  // TMA bulk copies of the contiguous chunk (see preprocess.cu)
+      if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_expect_tx(&s_bar, (uint32_t)(n * 4 * (3 + a.cov_floats + (NC > 0 ? a.col_floats : 0))));
+        tma_bulk_load(s_mean, g_mean, n * 12, &s_bar);
+        tma_bulk_load(s_cov, g_cov, n * a.cov_floats * 4, &s_bar);
+        if (NC > 0) tma_bulk_load(s_col, g_col, n * a.col_floats * 4, &s_bar);
+      }
+      __syncthreads();
+      mbar_wait(&s_bar, 0);
+    } else {
+      stage_in_bwd(s_mean, g_mean, n * 3, 3, 3);
+      stage_in_bwd(s_cov, g_cov, n * a.cov_floats, a.cov_floats, a.cov_floats);
+      if (NC > 0) stage_in_bwd(s_col, g_col, n * a.col_floats, a.col_floats, a.col_stride);
+      __syncthreads();
+    }
+  }
 
   float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (tid < n) {
