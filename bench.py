@@ -372,15 +372,27 @@ def run_ours(args):
         else:
             ach = amount / (ms_k * 1e-3) / 1e12
             stage_report[k] = {"ms": round(ms_k, 4), "bound": "fp32", "achieved": round(ach, 3), "unit": "TFLOP/s", "frac": round(ach / fp32_peak, 4)}
+    # DRAM traffic per launch from the committed ncu capture of this same workload (profiles/ncu_traffic.json)
+    traffic = {}
+    tpath = ROOT / "profiles" / "ncu_traffic.json"
+    if tpath.exists() and args.config == "C2T" and V == cfg.v_tgt:
+        tj = json.loads(tpath.read_text())
+        traffic = {k: v["dram_bytes_per_launch"] for k, v in tj.items() if isinstance(v, dict)}
+        if "sort_passes" in traffic:
+            traffic["sort_passes"] *= plan.sort_passes  # the stage is all passes
     dom = max(stage_report, key=lambda k: stage_report[k]["ms"]) if stage_report else None
     roofline = None
     if dom:
         r = stage_report[dom]
         roofline = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": round(hbm_peak if r["bound"] == "hbm" else fp32_peak, 2),
-                    "unit": r["unit"], "frac": r["frac"], "traffic": None, "ms": r["ms"],
+                    "unit": r["unit"], "frac": r["frac"], "traffic": traffic.get(dom), "ms": r["ms"],
+                    "algorithmic": alg[dom][1],
                     "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs" if r["bound"] == "hbm" else
                     f"148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock sampled under load)",
                     "share_of_step": round(r["ms"] / max(sum(v["ms"] for v in stage_report.values()), 1e-9), 4)}
+    for k, v in stage_report.items():
+        if k in traffic:
+            v["traffic"] = traffic[k]
     hbm_stages = {k: v for k, v in stage_report.items() if v["bound"] == "hbm"}
     dom_hbm = max(hbm_stages, key=lambda k: hbm_stages[k]["ms"]) if hbm_stages else None
 
