@@ -205,7 +205,9 @@ def run_ours(args):
     dataset_cfg = type("DatasetCfg", (), {"background_color": [0.0, 0.0, 0.0]})()
     decoder = get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), dataset_cfg).to(dev)
     # view sharding + ONE NCCL all-reduce of the flattened per-Gaussian gradients in the backward (identity at N=1)
-    sharded = ViewShardedDecoder(decoder, fused_reduce=(world > 1 and args.fused_reduce))
+    sharded = ViewShardedDecoder(decoder, fused_reduce=(world > 1 and args.fused_reduce), overlap_reduce=(world > 1 and args.overlap_reduce))
+    if getattr(sharded, "reducer", None) is not None and hasattr(sharded.reducer, "chunks") and os.environ.get("B200S_REDUCE_CHUNKS"):
+        sharded.reducer.chunks = int(os.environ["B200S_REDUCE_CHUNKS"])
     gnames = ("means", "covariances", "harmonics", "opacities")
 
     def step(t):
@@ -410,8 +412,8 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": _workload_name(cfg, scene_cpu, V), "views_per_gpu": V, "gaussians": N, "height": H, "width": W,
                        "l2": "inputs larger than L2 (Gaussians 472 MB + 64 B records per view)" if N * 160 > 126e6 else "inputs fit L2",
-                       "parallelism": f"view-sharded x{world}, Gaussians replicated" + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if sharded.reducer is not None and sharded.reducer.available
-                                        else ", NCCL all-reduce of per-Gaussian grads") if world > 1 else "")},
+                       "parallelism": f"view-sharded x{world}, Gaussians replicated" + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
+                                        else (", NCCL all-reduce of per-Gaussian grads" + (" in 2 chunks overlapped with the projection backward" if args.overlap_reduce else ""))) if world > 1 else "")},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_step_e, 4), "pinned_copy_bandwidth": pcie, "allocator_events": alloc_events,
                     "note": "3-stream pipeline: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i"},
@@ -440,6 +442,9 @@ def main():
     ap.add_argument("--config", default="C2T")
     ap.add_argument("--views", type=int, default=0, help="target views per GPU (default: the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--overlap-reduce", action="store_true",
+                    help="N>1: projection backward in 2 Gaussian ranges, each followed by an async NCCL all-reduce (measured: no "
+                         "consistent gain at N=2, 9.6-13 ms against a stable 9.85 ms for one all-reduce after the backward)")
     ap.add_argument("--fused-reduce", action="store_true",
                     help="N>1: sum the gradients inside the backward kernel over NVLS multicast (multimem.red) instead of one NCCL "
                          "all-reduce; measured SLOWER on B200 (one-shot multimem.red delivers every rank's data to every rank)")

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 4
+#define B200S_ABI_VERSION 5
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -155,6 +155,11 @@ typedef struct B200sGradIn { /* all fp32, OVERWRITTEN (summed over the views of 
                              kernel ADDS its result with multimem.red, so that after a barrier every GPU holds the sum over
                              all ranks -- the preprocess backward and the gradient all-reduce of view-sharded training are one
                              pass, the reduction happens in the NVSwitch. */
+  int32_t stages;         /* 0 = everything; else bit 0: compositing backward (fills the gradient records), bit 1: projection
+                             backward.  Lets the caller run the projection backward in Gaussian CHUNKS and start reducing each
+                             chunk's gradients across GPUs while the next chunk is computed. */
+  int32_t chunk_begin;    /* projection backward: first 256-Gaussian chunk of every scene to process ... */
+  int32_t chunk_count;    /* ... and how many (0 = all remaining) */
 } B200sGradIn;
 
 /* Pure host function: fills the plan for the given dimensions.  No CUDA calls. */

@@ -10,7 +10,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200splat.so"
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 B200S_OK, B200S_EBADARG, B200S_ECUDA = 0, 1, 3
 COV_3X3, COV_UPPER6 = 0, 1
@@ -76,6 +76,7 @@ class GradIn(C.Structure):
     _fields_ = [
         ("dL_dmeans", _f32p), ("dL_dcovariances", _f32p), ("dL_dharmonics", _f32p), ("dL_dcolors", _f32p),
         ("dL_dopacities", _f32p), ("dL_dmeans2D", _f32p), ("multicast", C.c_int32),
+        ("stages", C.c_int32), ("chunk_begin", C.c_int32), ("chunk_count", C.c_int32),
     ]
 
 

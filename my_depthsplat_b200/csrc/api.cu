@@ -212,8 +212,11 @@ int b200s_backward(const B200sScene* sc, const B200sViews* vw, const B200sPlan* 
   cudaStream_t stream = (cudaStream_t)stream_;
   const B200sStatus* st = reinterpret_cast<const B200sStatus*>(saved + pl->off_status);
   float* grad_rec = reinterpret_cast<float*>(scratch + pl->off_grad_rec);
+  const int stages = gin->stages ? gin->stages : 3;
+  cudaError_t e = cudaSuccess;
+  if (stages & 1) {
   stage_mark(B200S_STAGE_GRAD_ZERO, stream);
-  cudaError_t e = cudaMemsetAsync(grad_rec, 0, (size_t)vw->num_views * sc->num_gaussians * GREC_FLOATS * sizeof(float), stream);
+  e = cudaMemsetAsync(grad_rec, 0, (size_t)vw->num_views * sc->num_gaussians * GREC_FLOATS * sizeof(float), stream);
   if (e != cudaSuccess) return fail(e);
   CompArgs a;
   memset(&a, 0, sizeof(a));
@@ -227,6 +230,8 @@ int b200s_backward(const B200sScene* sc, const B200sViews* vw, const B200sPlan* 
   a.dL_dcolor = gout->dL_dcolor; a.dL_ddepth = gout->dL_ddepth; a.grad_rec = grad_rec;
   e = launch_composite_bwd(a, pl->tiles, vw->num_views, vw->depth_mode != B200S_DEPTH_NONE, stream);
   if (e != cudaSuccess) return fail(e);
+  }
+  if (!(stages & 2)) { stage_mark(B200S_STAGE_END, stream); return B200S_OK; }
   e = launch_preprocess_bwd(*sc, *vw, *pl, saved, scratch, *gin, stream);
   stage_mark(B200S_STAGE_END, stream);
   return e == cudaSuccess ? B200S_OK : fail(e);

@@ -21,6 +21,7 @@ struct PreBwdArgs {
   const float* grad_rec;  // [VV,N,12]
   float* dL_dmeans2D;     // [VV,N,3] or NULL
   const uint32_t* overflow;
+  int chunk_begin, chunk_count;  // range of 256-Gaussian chunks (per scene) this launch covers
 };
 
 __device__ __forceinline__ void stage_in_bwd(float* dst, const float* __restrict__ src, int count, int k, int stride) {
@@ -79,8 +80,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
   constexpr int DEG = NC == 16 ? 3 : (NC == 9 ? 2 : (NC == 4 ? 1 : 0));
   constexpr int NACC = NC > 0 ? 3 * NC : 3;
   const int tid = threadIdx.x;
-  const int chunks = (a.N + PRE_THREADS - 1) / PRE_THREADS;
-  const int scene = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int scene = blockIdx.x / a.chunk_count, chunk = a.chunk_begin + blockIdx.x % a.chunk_count;
   const int i0 = chunk * PRE_THREADS;
   const int n = min(PRE_THREADS, a.N - i0);
   const long long g0 = (long long)scene * a.N + i0;
@@ -317,7 +317,10 @@ cudaError_t launch_preprocess_bwd(const B200sScene& sc, const B200sViews& vw, co
   a.dL_dmeans2D = gin.dL_dmeans2D;
   a.overflow = &reinterpret_cast<const B200sStatus*>(saved + plan.off_status)->overflow;
   const int chunks = (sc.num_gaussians + PRE_THREADS - 1) / PRE_THREADS;
-  const int blocks = chunks * sc.num_scenes;
+  a.chunk_begin = gin.chunk_begin > 0 ? gin.chunk_begin : 0;
+  a.chunk_count = gin.chunk_count > 0 ? gin.chunk_count : chunks - a.chunk_begin;
+  if (a.chunk_begin + a.chunk_count > chunks) a.chunk_count = chunks - a.chunk_begin;
+  const int blocks = a.chunk_count * sc.num_scenes;
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)PRE_THREADS * (3 + a.cov_floats + a.col_stride) * sizeof(float);
   const int nc = sc.colors_precomp ? 0 : (sc.sh_degree + 1) * (sc.sh_degree + 1);

@@ -141,6 +141,32 @@ class FusedGradReducer:
         self._cur.barrier(channel=1)
 
 
+class ChunkedAllReducer:
+    """Sum of the per-Gaussian gradients over the ranks, OVERLAPPED with the kernel that produces them: the
+    rasterizer runs its projection backward in ``chunks`` Gaussian ranges and hands each finished range to an
+    asynchronous NCCL all-reduce (NCCL's own stream), so the NVLink transfer of range k runs under the
+    computation of range k+1.  The backward returns after waiting (on the stream) for all of them."""
+
+    chunked = True
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, chunks: int = 2):
+        self.group = group
+        self.chunks = max(1, int(chunks))
+        self.available = dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def reduce_async(self, tensors):
+        """One NCCL group call for the (up to four) gradient ranges of a chunk -> list of work handles."""
+        tensors = [t for t in tensors if t.numel() > 0]
+        try:
+            from torch.distributed.distributed_c10d import _coalescing_manager
+            with _coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
+                for t in tensors:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return [cm]
+        except (ImportError, TypeError):
+            return [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for t in tensors]
+
+
 class ViewShardedDecoder(torch.nn.Module):
     """Wraps a decoder (``DecoderSplattingCUDA`` or anything with its ``forward`` signature): every rank
     renders its contiguous slice of the target views of every scene; per-Gaussian gradients are summed
@@ -148,11 +174,16 @@ class ViewShardedDecoder(torch.nn.Module):
     (inference); otherwise the local slice (training: the loss is computed on the local views)."""
 
     def __init__(self, decoder: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, gather: bool = False,
-                 fused_reduce: bool = False):
+                 fused_reduce: bool = False, overlap_reduce: bool = False):
         super().__init__()
         self.decoder = decoder
         self.group = group
         self.gather = gather
+        # overlap_reduce: chunked projection backward with one async NCCL all-reduce per chunk (ChunkedAllReducer)
+        if overlap_reduce and not fused_reduce and dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(decoder, "grad_reducer"):
+            self.reducer = ChunkedAllReducer(group)
+            decoder.grad_reducer = self.reducer
+            return
         # fused_reduce: the backward kernel reduces across ranks itself (NVLS multimem), no all-reduce afterwards
         self.reducer = None
         if fused_reduce and dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(decoder, "grad_reducer"):

@@ -281,22 +281,42 @@ class _Rasterize(torch.autograd.Function):
         scratch = _scratch(dev, plan.scratch_bytes)
         gout = _lib.GradOut(_ptr(g_color), _ptr(g_depth))
         reducer = vp.grad_reducer if (vp.grad_reducer is not None and getattr(vp.grad_reducer, "available", False)) else None
-        if reducer is not None:
+        out = _lib.Out(None, None, None, 0)
+
+        def call(gin):
+            _lib.check(L.b200s_backward(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(), C.byref(out),
+                                        C.byref(gout), C.byref(gin), stream), "b200s_backward")
+
+        if reducer is not None and not getattr(reducer, "chunked", False):
             # outputs are NVLS multicast addresses: the kernel ADDS into every rank's (zeroed) replica
             (d_means, d_covs, d_colors, d_op), mc = reducer.begin([means.shape, covs.shape, colors.shape, opacities.shape], dev)
-            gin = _lib.GradIn(mc[0], mc[1], mc[2] if use_sh else None, None if use_sh else mc[2], mc[3], _ptr(d_m2d), 1)
+            call(_lib.GradIn(mc[0], mc[1], mc[2] if use_sh else None, None if use_sh else mc[2], mc[3], _ptr(d_m2d), 1, 0, 0, 0))
+            reducer.end()
         else:
             d_means = torch.empty_like(means)
             d_covs = torch.empty_like(covs)
             d_colors = torch.empty_like(colors)
             d_op = torch.empty_like(opacities)
-            gin = _lib.GradIn(_ptr(d_means), _ptr(d_covs), _ptr(d_colors) if use_sh else None, None if use_sh else _ptr(d_colors),
-                              _ptr(d_op), _ptr(d_m2d), 0)
-        out = _lib.Out(None, None, None, 0)
-        _lib.check(L.b200s_backward(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(), C.byref(out),
-                                    C.byref(gout), C.byref(gin), stream), "b200s_backward")
-        if reducer is not None:
-            reducer.end()
+            mk = lambda stages, c0, cn: _lib.GradIn(_ptr(d_means), _ptr(d_covs), _ptr(d_colors) if use_sh else None,
+                                                    None if use_sh else _ptr(d_colors), _ptr(d_op), _ptr(d_m2d), 0, stages, c0, cn)
+            if reducer is None:
+                call(mk(0, 0, 0))
+            else:
+                # compositing backward once, then the projection backward range by range; every finished range
+                # goes to an async NCCL all-reduce that runs under the next range's kernel
+                call(mk(1, 0, 0))
+                total = (N + 255) // 256
+                nch = reducer.chunks if means.shape[0] == 1 else 1  # ranges are contiguous only within one scene
+                per = (total + nch - 1) // nch
+                works = []
+                for c0 in range(0, total, per):
+                    cn = min(per, total - c0)
+                    call(mk(2, c0, cn))
+                    g0, g1 = c0 * 256, min(N, (c0 + cn) * 256)
+                    parts = [d_means, d_covs, d_colors, d_op] if nch == 1 else [t[:, g0:g1] for t in (d_means, d_covs, d_colors, d_op)]
+                    works += reducer.reduce_async(parts)
+                for w in works:
+                    w.wait()
         return d_means, d_covs, d_colors, d_op, d_m2d, None, None, None, None, None, None
 
 

@@ -40,13 +40,15 @@ nccl = grads(ViewShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatt
 fused_dec = ViewShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), fused_reduce=True)
 fused = [t.clone() for t in grads(fused_dec, (lo, hi))]
 fused2 = [t.clone() for t in grads(fused_dec, (lo, hi))]   # second call: the other symmetric buffer
+ovl_dec = ViewShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), overlap_reduce=True)
+ovl = grads(ovl_dec, (lo, hi))
 torch.cuda.synchronize()
 ok = True
-for nm, s, a, b, c in zip(("means", "covariances", "harmonics", "opacities"), single, nccl, fused, fused2):
+for nm, s, a, b, c, d in zip(("means", "covariances", "harmonics", "opacities"), single, nccl, fused, fused2, ovl):
     scale = float(s.abs().max())
-    e_n, e_f, e_f2 = (float((x - s).abs().max()) / scale for x in (a, b, c))
-    print(f"rank {rank} {nm:12s} |nccl - single| {e_n:.2e}  |fused - single| {e_f:.2e}  |fused(2nd) - single| {e_f2:.2e}", flush=True)
-    ok &= e_n < 2e-4 and e_f < 2e-4 and e_f2 < 2e-4
+    e_n, e_f, e_f2, e_o = (float((x - s).abs().max()) / scale for x in (a, b, c, d))
+    print(f"rank {rank} {nm:12s} |nccl - single| {e_n:.2e}  |fused - single| {e_f:.2e}  |fused(2nd) - single| {e_f2:.2e}  |overlapped - single| {e_o:.2e}", flush=True)
+    ok &= e_n < 2e-4 and e_f < 2e-4 and e_f2 < 2e-4 and e_o < 2e-4
 print(f"rank {rank} fused reducer active: {fused_dec.reducer is not None and fused_dec.reducer.available}  {'OK' if ok else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
