@@ -448,7 +448,13 @@ def main():
     ap.add_argument("--fused-reduce", action="store_true",
                     help="N>1: sum the gradients inside the backward kernel over NVLS multicast (multimem.red) instead of one NCCL "
                          "all-reduce; measured SLOWER on B200 (one-shot multimem.red delivers every rank's data to every rank)")
+    ap.add_argument("--knob", action="append", default=[], metavar="K=V",
+                    help="kernel variant switch for A/B runs (b200s_debug_set): 0 histogram, 1 sort ranking, 2 backward reduction")
     args = ap.parse_args()
+    for kv in args.knob:
+        from my_depthsplat_b200 import _lib
+        k, v = kv.split("=")
+        _lib.load().b200s_debug_set(int(k), int(v))
     if args.impl == "reference":
         run_reference(args)
     else:
