@@ -14,6 +14,8 @@ while [ $# -gt 0 ]; do
     benchquick)
       python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
       cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err ;;
+    baseline)
+      python -m pytest tests/test_gpu_baseline.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/baseline_tests.log; echo "pytest rc=$?" >> gpurun_out/baseline_tests.log; tail -15 gpurun_out/baseline_tests.log ;;
     ncu-list)
       # same command line run plain first, directly before, no pipe
       NCU_CMD="python bench.py --steps 1 --warmup 3 --no-cpu"

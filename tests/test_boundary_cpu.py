@@ -112,3 +112,23 @@ def test_product_never_imports_the_oracle():
     for f in (ROOT / "my_depthsplat_b200").rglob("*"):
         if f.suffix in (".py", ".cu", ".cuh", ".h") and f.is_file():
             assert not bad.search(f.read_text()), f
+
+
+def test_product_never_imports_the_gpu_comparator():
+    """baseline/ (the upstream-style restatement with CUB that bench.py times next to the product) is a comparator:
+    nothing under my_depthsplat_b200/ may import, include or load it; and it uses none of the product's kernels."""
+    bad = re.compile(r"^\s*(from\s+baseline|import\s+baseline|#\s*include\s+[\"<].*baseline)|libupstream_style|cub/", re.M)
+    for f in (ROOT / "my_depthsplat_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h") and f.is_file():
+            assert not bad.search(f.read_text()), f
+    src = (ROOT / "baseline" / "upstream_style.cu").read_text()
+    assert "my_depthsplat_b200" not in src and "b200splat" not in src
+
+
+def test_gpu_comparator_library_loads():
+    from baseline import upstream_ext
+    if not upstream_ext.available():
+        pytest.skip("baseline/_build/libupstream_style.so not built (make -C baseline)")
+    L = upstream_ext.load()
+    for name in ("ups_preprocess", "ups_bin_render", "ups_backward", "ups_scan_temp_bytes", "ups_sort_temp_bytes"):
+        assert hasattr(L, name)

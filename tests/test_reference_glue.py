@@ -121,3 +121,25 @@ def test_signatures_match_the_reference():
     ref_projection = importlib.import_module("src.geometry.projection")
     K = make_scene("small").intrinsics.reshape(-1, 3, 3)
     assert torch.equal(ref_projection.get_fov(K), get_fov(K))
+
+
+@pytest.mark.parametrize("name,depth_mode", [("tiny", "depth"), ("small", None)])
+def test_comparator_glue_restates_the_reference_glue(name, depth_mode):
+    """baseline/per_view_glue.py (what bench.py's gpu_baseline runs over the upstream-style CUDA comparator) executes the
+    reference's glue: same images and gradients as the unmodified reference file, both over the CPU oracle."""
+    from baseline import per_view_glue
+    from oracle import ext_compat
+    cs = load_reference_cuda_splatting(ext_compat)
+    scene = make_scene(name)
+    g1, g2 = leaf_gaussians(scene), leaf_gaussians(scene)
+    c1, d1 = _ref_render(cs, scene, g1, depth_mode)
+    c2, d2 = per_view_glue.decoder_forward(ext_compat, g2, scene.extrinsics, scene.intrinsics, scene.near, scene.far,
+                                           scene.image_shape, scene.background, depth_mode)
+    assert torch.equal(c1, c2)
+    loss1, loss2 = (c1 * scene.grad_color).sum(), (c2 * scene.grad_color).sum()
+    if depth_mode is not None:
+        assert torch.equal(d1, d2)
+        loss1, loss2 = loss1 + (d1 * scene.grad_depth).sum(), loss2 + (d2 * scene.grad_depth).sum()
+    loss1.backward(); loss2.backward()
+    for a, b in ((g1.means, g2.means), (g1.covariances, g2.covariances), (g1.harmonics, g2.harmonics), (g1.opacities, g2.opacities)):
+        assert torch.equal(a.grad, b.grad)

@@ -54,8 +54,32 @@ def run(name, steps=5, warmup=2):
     st = {k: round(v, 3) for k, v in _lib.profile_read().items() if v > 0.0005 and k != "end"}
     _lib.profile_enable(False)
     pairs = R.last_stats.num_pairs
+    # the upstream-style GPU comparator (baseline/) on the same scene: per-view calls, V-fold replication, CUB sort
+    base_ms = None
+    if name != "C5":  # the comparator's 32-bit pair offsets cannot hold the stress scene
+        from baseline import per_view_glue, upstream_ext
+        from my_depthsplat_b200.types import Gaussians
+
+        def base_step():
+            leaves = [t.detach().requires_grad_(backward) for t in (g.means, g.covariances, g.harmonics, g.opacities)]
+            with torch.set_grad_enabled(backward):
+                color, depth = per_view_glue.decoder_forward(upstream_ext, Gaussians(*leaves), sc.extrinsics, sc.intrinsics, sc.near, sc.far,
+                                                             (H, W), sc.background, depth_mode)
+            if backward:
+                outs, gouts = [color], [sc.grad_color]
+                if depth is not None:
+                    outs.append(depth); gouts.append(sc.grad_depth)
+                torch.autograd.grad(outs, leaves, gouts)
+
+        base_step(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            base_step()
+        e1.record(); torch.cuda.synchronize()
+        base_ms = e0.elapsed_time(e1) / 3
     out = {"config": name, "scenes": B, "gaussians": g.means.shape[1], "views": V, "HxW": f"{H}x{W}", "mode": ("fwd+bwd" if backward else "fwd") + ("+depth" if depth_mode else ""),
-           "ms_per_call": round(ms, 3), "Mpix_s": round(B * V * H * W / ms / 1e3, 1), "pairs_last_call": pairs, "stages_ms": st,
+           "ms_per_call": round(ms, 3), "Mpix_s": round(B * V * H * W / ms / 1e3, 1),
+           "upstream_style_ms": None if base_ms is None else round(base_ms, 3), "speedup": None if base_ms is None else round(base_ms / ms, 2), "pairs_last_call": pairs, "stages_ms": st,
            "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2), "setup_s": round(time.time() - t0, 1)}
     print(json.dumps(out), flush=True)
     del sc, g
