@@ -50,7 +50,14 @@ def _worker(rank, world, port, result_dir):
         with torch.no_grad():
             full = D.ViewShardedDecoder(OracleDecoder(), gather=True).forward(
                 g, scene.extrinsics, scene.intrinsics, scene.near, scene.far, scene.image_shape, depth_mode="depth")
-        torch.save({"color": full.color, "depth": full.depth, "grads": [g.means.grad, g.covariances.grad, g.harmonics.grad, g.opacities.grad]},
+        # --- clip rendering: views sharded, chunks of 1 view, frames gathered
+        from my_depthsplat_b200.video import render_clip
+        clip = render_clip(OracleDecoder(), g, scene.extrinsics, scene.intrinsics, scene.near, scene.far, scene.image_shape,
+                           chunk_size=1, depth_mode="depth", gather=True)
+        local = render_clip(OracleDecoder(), g, scene.extrinsics, scene.intrinsics, scene.near, scene.far, scene.image_shape, chunk_size=None)
+        assert local.color.shape[1] == hi - lo and local.depth is None
+        assert torch.equal(local.color, clip.color[:, lo:hi])
+        torch.save({"color": full.color, "depth": full.depth, "clip_color": clip.color, "clip_depth": clip.depth, "grads": [g.means.grad, g.covariances.grad, g.harmonics.grad, g.opacities.grad]},
                    Path(result_dir) / f"rank{rank}.pt")
     finally:
         dist.destroy_process_group()
@@ -83,6 +90,7 @@ def test_view_sharded_decoder_two_ranks(tmp_path):
     ((c * scene.grad_color).sum() + (d * scene.grad_depth).sum()).backward()
     for r in res:
         assert torch.equal(r["color"], c.detach()) and torch.equal(r["depth"], d.detach())  # gathered frames = 1-process frames
+        assert torch.equal(r["clip_color"], c.detach()) and torch.equal(r["clip_depth"], d.detach())  # chunked clip too
         for got, ref in zip(r["grads"], (g.means.grad, g.covariances.grad, g.harmonics.grad, g.opacities.grad)):
             torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-6 * float(ref.abs().max()))  # sum order differs
     for a, b in zip(res[0]["grads"], res[1]["grads"]):
