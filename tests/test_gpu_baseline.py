@@ -15,6 +15,8 @@ pytestmark = pytest.mark.gpu
 
 def _baseline(scene_gpu, leaves, depth_mode=None):
     from baseline import per_view_glue, upstream_ext
+    if not upstream_ext.available():
+        pytest.skip("comparator not built (make -C baseline); it is not part of the product")
     return per_view_glue.decoder_forward(upstream_ext, Gaussians(*leaves), scene_gpu.extrinsics, scene_gpu.intrinsics, scene_gpu.near,
                                          scene_gpu.far, scene_gpu.image_shape, scene_gpu.background, depth_mode)
 
