@@ -198,15 +198,18 @@ __device__ __forceinline__ bool bwd_entry(const float4 h0, const float4 h1, cons
     dL_dalpha *= s.T;
     s.last_alpha = alpha;
     dL_dalpha -= s.T_final * inv * s.bg_dot;
-    const float dL_dG = h1.w * dL_dalpha;
-    const float gdx = G * dx, gdy = G * dy;
-    out[0] = dL_dG * (-gdx * h1.x - gdy * h1.y) * half_w;
-    out[1] = dL_dG * (-gdy * h1.z - gdx * h1.y) * half_h;
-    const float m = -0.5f * dL_dG;
-    out[2] = m * gdx * dx;
-    out[3] = m * gdx * dy;
-    out[4] = m * gdy * dy;
-    out[5] = G * dL_dalpha;
+    // moments of q = G * dL/dalpha over the pixels; the per-Gaussian factors (opacity, conic, half extent of the
+    // image, -1/2) are applied once per (view, Gaussian) by the projection backward instead of once per pixel:
+    //   dL/dmean2D = opacity * half * (-A*S_x - B*S_y, -C*S_y - B*S_x),  dL/dconic = -opacity/2 * (S_xx, S_xy, S_yy),
+    //   dL/dopacity = S_1
+    const float q = G * dL_dalpha;
+    const float qx = q * dx, qy = q * dy;
+    out[0] = qx;
+    out[1] = qy;
+    out[2] = qx * dx;
+    out[3] = qx * dy;
+    out[4] = qy * dy;
+    out[5] = q;
   }
   return true;
 }

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
   }
 
   float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float op = tid < n ? __ldg(sc.opacities + g0 + tid) : 0.f;
   if (tid < n) {
     mraw[0] = s_mean[tid * 3]; mraw[1] = s_mean[tid * 3 + 1]; mraw[2] = s_mean[tid * 3 + 2];
     const float* cp = s_cov + tid * a.cov_floats;
@@ -139,10 +140,11 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
     const float4* gp = reinterpret_cast<const float4*>(a.grad_rec + ri * GREC_FLOATS);
     float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, g2v = g0v;
     if (radius > 0) { g0v = __ldg(gp); g1v = __ldg(gp + 1); g2v = __ldg(gp + 2); }
-    if (a.dL_dmeans2D) { float* o = a.dL_dmeans2D + ri * 3; o[0] = g0v.x; o[1] = g0v.y; o[2] = 0.f; }
-    if (radius <= 0) continue;
+    if (radius <= 0) {
+      if (a.dL_dmeans2D) { float* o = a.dL_dmeans2D + ri * 3; o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
+      continue;
+    }
     const uint32_t flags = __float_as_uint(q3.w);
-    const float g2x = g0v.x, g2y = g0v.y, gcx = g0v.z, gcy = g0v.w, gcz = g1v.x;
     dop += g1v.y;
     const float m[3] = {__fmul_rn(mraw[0], vp.s), __fmul_rn(mraw[1], vp.s), __fmul_rn(mraw[2], vp.s)};
     float c6[6];
@@ -153,7 +155,20 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
     Cov2D q;
     compute_cov2d(m, c6, vp, q);
     const float ca = q.a, cb = q.b, cc = q.c;
-    const float denom = ca * cc - cb * cb;
+    const float denom = __fsub_rn(__fmul_rn(ca, cc), __fmul_rn(cb, cb));
+    // the compositing backward left the pixel moments S_x, S_y, S_xx, S_xy, S_yy of q = G * dL/dalpha (composite.cu):
+    // apply the per-Gaussian factors here.  The conic is the forward's, bit for bit (same cov2D, same 1/det).
+    float g2x, g2y, gcx, gcy, gcz;
+    {
+      const float det_inv = __frcp_rn(denom);
+      const float cA = __fmul_rn(cc, det_inv), cB = __fmul_rn(-cb, det_inv), cC = __fmul_rn(ca, det_inv);
+      const float sx = g0v.x, sy = g0v.y;
+      g2x = op * (0.5f * (float)a.W) * (-cA * sx - cB * sy);
+      g2y = op * (0.5f * (float)a.H) * (-cC * sy - cB * sx);
+      const float mh = -0.5f * op;
+      gcx = mh * g0v.z; gcy = mh * g0v.w; gcz = mh * g1v.x;
+    }
+    if (a.dL_dmeans2D) { float* o = a.dL_dmeans2D + ri * 3; o[0] = g2x; o[1] = g2y; o[2] = 0.f; }
     const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
     float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
     float dm[3];  // gradient w.r.t. the NORMALISED mean
