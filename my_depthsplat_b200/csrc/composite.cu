@@ -159,10 +159,15 @@ __device__ __forceinline__ void butterfly_step(float* v, const uint32_t lane) {
   }
 }
 
+// Per-pixel state of the reverse walk.  The reference recurrence keeps, per channel, the colour accumulated BEHIND the
+// current entry (accum = last_alpha * last_colour + (1 - last_alpha) * accum) and contracts it with dL/dpixel; the
+// contraction commutes with the recurrence, so only its scalar image is carried:
+//   E = sum_ch accum[ch] * dpix[ch]   ->   E' = last_alpha * D_last + (1 - last_alpha) * E,   D = sum_ch colour[ch] * dpix[ch]
 template <bool DEPTH>
 struct PixState {
-  float T, T_final, last_alpha, bg_dot;
-  float accum[DEPTH ? 4 : 3], last_col[DEPTH ? 4 : 3], dpix[DEPTH ? 4 : 3];
+  float T, tb, last_alpha;   // tb = final_T * sum_ch bg[ch] * dpix[ch]
+  float E, D_last;
+  float dpix[DEPTH ? 4 : 3];
   uint32_t last_contributor;
 };
 
@@ -187,17 +192,16 @@ __device__ __forceinline__ bool bwd_entry(const float4 h0, const float4 h1, cons
     s.T = s.T * inv;
     const float w = alpha * s.T;
     const float col[4] = {h2.x, h2.y, h2.z, h2.w};
-    float dL_dalpha = 0.f;
+    float D = 0.f;
 #pragma unroll
     for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) {
-      s.accum[ch] = s.last_alpha * s.last_col[ch] + (1.f - s.last_alpha) * s.accum[ch];
-      s.last_col[ch] = col[ch];
-      dL_dalpha += (col[ch] - s.accum[ch]) * s.dpix[ch];
+      D += col[ch] * s.dpix[ch];
       out[6 + ch] = w * s.dpix[ch];
     }
-    dL_dalpha *= s.T;
+    s.E = s.last_alpha * s.D_last + (1.f - s.last_alpha) * s.E;
+    s.D_last = D;
     s.last_alpha = alpha;
-    dL_dalpha -= s.T_final * inv * s.bg_dot;
+    const float dL_dalpha = (D - s.E) * s.T - s.tb * inv;
     // moments of q = G * dL/dalpha over the pixels; the per-Gaussian factors (opacity, conic, half extent of the
     // image, -1/2) are applied once per (view, Gaussian) by the projection backward instead of once per pixel:
     //   dL/dmean2D = opacity * half * (-A*S_x - B*S_y, -C*S_y - B*S_x),  dL/dconic = -opacity/2 * (S_xx, S_xy, S_yy),
@@ -214,8 +218,8 @@ __device__ __forceinline__ bool bwd_entry(const float4 h0, const float4 h1, cons
   return true;
 }
 
-template <bool DEPTH>
-__global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_kernel(const CompArgs a) {
+template <bool DEPTH, int MIN_CTAS>
+__global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const CompArgs a) {
   __shared__ float4 s_q0[WARPS][32], s_q1[WARPS][32], s_q2[WARPS][32];
   __shared__ uint32_t s_pos[WARPS][32], s_id[WARPS][32];
   if (*a.overflow) return;
@@ -232,21 +236,21 @@ __global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_kernel(const CompAr
   const size_t pid = (size_t)g.py * a.W + g.px;
 
   PixState<DEPTH> s;
-  s.T_final = g.inside ? a.final_T[(size_t)view * HW + pid] : 0.f;
-  s.T = s.T_final;
+  s.T = g.inside ? a.final_T[(size_t)view * HW + pid] : 0.f;
   s.last_contributor = g.inside ? a.n_contrib[(size_t)view * HW + pid] : 0u;
-  s.last_alpha = 0.f;
-  s.bg_dot = 0.f;
+  s.last_alpha = 0.f; s.E = 0.f; s.D_last = 0.f;
+  float bg_dot = 0.f;
 #pragma unroll
-  for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) { s.accum[ch] = 0.f; s.last_col[ch] = 0.f; s.dpix[ch] = 0.f; }
+  for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) s.dpix[ch] = 0.f;
   if (g.inside) {
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
       s.dpix[ch] = a.dL_dcolor[((size_t)view * 3 + ch) * HW + pid];
-      s.bg_dot += a.bg[view * 3 + ch] * s.dpix[ch];
+      bg_dot += a.bg[view * 3 + ch] * s.dpix[ch];
     }
     if (DEPTH) s.dpix[3] = a.dL_ddepth[(size_t)view * HW + pid];
   }
+  s.tb = s.T * bg_dot;
   // entries at list positions >= the warp's max(last_contributor) are needed by none of its pixels
   uint32_t wmax = s.last_contributor;
 #pragma unroll
@@ -325,8 +329,9 @@ cudaError_t launch_composite_bwd(const CompArgs& a, int tiles, int views, bool d
   dim3 grid(tiles, views);
   stage_mark(B200S_STAGE_COMP_BWD, stream);
   count_launches(1);
-  if (depth) composite_bwd_kernel<true><<<grid, TILE_PIX, 0, stream>>>(a);
-  else composite_bwd_kernel<false><<<grid, TILE_PIX, 0, stream>>>(a);
+  // three CTAs per SM (80 registers): four (64 registers, 32 B of spills) measured 3.31 ms against 2.91 ms
+  if (depth) composite_bwd_kernel<true, 3><<<grid, TILE_PIX, 0, stream>>>(a);
+  else composite_bwd_kernel<false, 3><<<grid, TILE_PIX, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
