@@ -171,57 +171,72 @@ struct PixState {
   uint32_t last_contributor;
 };
 
+// A compacted hit as the backward keeps it in the warp's shared-memory slots: everything one entry needs behind ONE
+// base address (the loop index is warp-uniform, so the loads are broadcasts with immediate offsets).
+struct __align__(16) BwdSlot {
+  float4 q1;   // (A, B, C, opacity)
+  float4 q2;   // (r, g, b, zc)
+  float x, y;
+  uint32_t pos, id;
+};
+
+__device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP; the argument is 1 - alpha in [0.01, 1]
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // One list entry on the warp's 32 pixels; writes this pixel's 10 partial gradients to out[0..9].
 // Returns (warp-uniform) whether ANY pixel of the warp received a contribution: a quarter of the entries
 // that pass the bounding-box cull touch no pixel that is still "alive" at that list position, and they are
-// dropped before the cross-lane reduction.  All 32 lanes must call.
-// h0 = (x, y, ex, ey)  h1 = (A, B, C, opacity)  h2 = (r, g, b, zc)
+// dropped before the cross-lane reduction.  All 32 lanes must call.  Branch-free below the vote: a lane the entry
+// does not reach runs the same arithmetic with alpha = 0 (T, the weights and q come out unchanged / zero) and keeps
+// its recurrence state through selects.
 template <bool DEPTH>
-__device__ __forceinline__ bool bwd_entry(const float4 h0, const float4 h1, const float4 h2, const uint32_t pos, PixState<DEPTH>& s,
-                                          const TileGeom& g, const float half_w, const float half_h, float* out) {
-  const float dx = __fsub_rn(h0.x, g.pfx), dy = __fsub_rn(h0.y, g.pfy);
+__device__ __forceinline__ bool bwd_entry(const BwdSlot* __restrict__ h, PixState<DEPTH>& s, const TileGeom& g, float* out) {
+  const float4 h1 = h->q1;
+  const float dx = __fsub_rn(h->x, g.pfx), dy = __fsub_rn(h->y, g.pfy);
   const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
   const float G = expf(power);
   const float alpha = fminf(ALPHA_MAX, __fmul_rn(h1.w, G));
-  const bool live = pos < s.last_contributor && power <= 0.0f && alpha >= ALPHA_MIN;
+  const bool live = h->pos < s.last_contributor && power <= 0.0f && alpha >= ALPHA_MIN;
   if (!__any_sync(0xffffffffu, live)) return false;
+  const float4 h2 = h->q2;
+  const float a_eff = live ? alpha : 0.f;
+  const float inv = rcp_approx(1.f - a_eff);  // exactly 1 for a_eff = 0
+  s.T = s.T * inv;
+  const float w = a_eff * s.T;
+  const float col[4] = {h2.x, h2.y, h2.z, h2.w};
+  float D = 0.f;
 #pragma unroll
-  for (int k = 0; k < 10; k++) out[k] = 0.f;
-  if (live) {
-    const float inv = __fdividef(1.f, 1.f - alpha);
-    s.T = s.T * inv;
-    const float w = alpha * s.T;
-    const float col[4] = {h2.x, h2.y, h2.z, h2.w};
-    float D = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) {
-      D += col[ch] * s.dpix[ch];
-      out[6 + ch] = w * s.dpix[ch];
-    }
-    s.E = s.last_alpha * s.D_last + (1.f - s.last_alpha) * s.E;
-    s.D_last = D;
-    s.last_alpha = alpha;
-    const float dL_dalpha = (D - s.E) * s.T - s.tb * inv;
-    // moments of q = G * dL/dalpha over the pixels; the per-Gaussian factors (opacity, conic, half extent of the
-    // image, -1/2) are applied once per (view, Gaussian) by the projection backward instead of once per pixel:
-    //   dL/dmean2D = opacity * half * (-A*S_x - B*S_y, -C*S_y - B*S_x),  dL/dconic = -opacity/2 * (S_xx, S_xy, S_yy),
-    //   dL/dopacity = S_1
-    const float q = G * dL_dalpha;
-    const float qx = q * dx, qy = q * dy;
-    out[0] = qx;
-    out[1] = qy;
-    out[2] = qx * dx;
-    out[3] = qx * dy;
-    out[4] = qy * dy;
-    out[5] = q;
+  for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) {
+    D += col[ch] * s.dpix[ch];
+    out[6 + ch] = w * s.dpix[ch];
   }
+  if (!DEPTH) out[9] = 0.f;
+  const float E = s.last_alpha * s.D_last + (1.f - s.last_alpha) * s.E;
+  s.E = live ? E : s.E;
+  s.D_last = live ? D : s.D_last;
+  s.last_alpha = live ? alpha : s.last_alpha;
+  const float dL_dalpha = (D - E) * s.T - s.tb * inv;
+  // moments of q = G * dL/dalpha over the pixels; the per-Gaussian factors (opacity, conic, half extent of the
+  // image, -1/2) are applied once per (view, Gaussian) by the projection backward instead of once per pixel:
+  //   dL/dmean2D = opacity * half * (-A*S_x - B*S_y, -C*S_y - B*S_x),  dL/dconic = -opacity/2 * (S_xx, S_xy, S_yy),
+  //   dL/dopacity = S_1
+  const float q = live ? G * dL_dalpha : 0.f;
+  const float qx = q * dx, qy = q * dy;
+  out[0] = qx;
+  out[1] = qy;
+  out[2] = qx * dx;
+  out[3] = qx * dy;
+  out[4] = qy * dy;
+  out[5] = q;
   return true;
 }
 
 template <bool DEPTH, int MIN_CTAS>
 __global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const CompArgs a) {
-  __shared__ float4 s_q0[WARPS][32], s_q1[WARPS][32], s_q2[WARPS][32];
-  __shared__ uint32_t s_pos[WARPS][32], s_id[WARPS][32];
+  __shared__ BwdSlot s_slot[WARPS][32];
   if (*a.overflow) return;
   const int tile = blockIdx.x, view = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -231,9 +246,11 @@ __global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const
   const TileGeom g = tile_geom(tile, a.grid_x, a.H, a.W);
   const Rec* __restrict__ vrec = a.rec + (size_t)view * a.N;
   const uint32_t* __restrict__ list = a.vals + range.x;
-  float* __restrict__ grec = a.grad_rec + (size_t)view * a.N * GREC_FLOATS;
   const size_t HW = (size_t)a.H * a.W;
   const size_t pid = (size_t)g.py * a.W + g.px;
+  // after the reduction lane l holds value l of the batch: component c of entry e = l / 10
+  const int red_e = lane / 10, red_c = lane - 10 * red_e;
+  float* __restrict__ grec_lane = a.grad_rec + (size_t)view * a.N * GREC_FLOATS + red_c;
 
   PixState<DEPTH> s;
   s.T = g.inside ? a.final_T[(size_t)view * HW + pid] : 0.f;
@@ -256,10 +273,10 @@ __global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
   if (wmax == 0) return;
-  const float half_w = 0.5f * (float)a.W, half_h = 0.5f * (float)a.H;
 
   // walk positions wmax-1 ... 0; lane l of a chunk starting at `top` holds position top-1-l, so that the
   // compacted slots ascend as the list is walked back to front
+  BwdSlot* const slots = s_slot[warp];
   int top = (int)wmax;
   uint32_t id_cur = top - 1 - lane >= 0 ? __ldg(list + (top - 1 - lane)) : 0u;
   uint32_t id_nxt = top - 33 - lane >= 0 ? __ldg(list + (top - 33 - lane)) : 0u;
@@ -276,29 +293,29 @@ __global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const
     const uint32_t mask = __ballot_sync(0xffffffffu, hit);
     if (mask == 0) continue;
     if (hit) {
-      const int slot = __popc(mask & lt);
+      BwdSlot* d = slots + __popc(mask & lt);
       const float4* r = reinterpret_cast<const float4*>(vrec + id);
-      s_q0[warp][slot] = q0; s_q1[warp][slot] = __ldg(r + 1); s_q2[warp][slot] = __ldg(r + 2);
-      s_pos[warp][slot] = (uint32_t)pos; s_id[warp][slot] = id;
+      d->q1 = __ldg(r + 1); d->q2 = __ldg(r + 2);
+      d->x = q0.x; d->y = q0.y; d->pos = (uint32_t)pos; d->id = id;
     }
     __syncwarp();
     const int nh = __popc(mask);
     // batches of three NON-EMPTY entries: walk the compacted slots in order, keep an entry only if some pixel
-    // of the warp received a contribution from it
+    // of the warp received a contribution from it (k and nh are warp-uniform: they live in uniform registers)
     for (int k = 0; k < nh;) {
       float v[32];
       uint32_t id0 = 0xffffffffu, id1 = 0xffffffffu, id2 = 0xffffffffu;
       bool f = false;
-      while (k < nh && !f) { f = bwd_entry<DEPTH>(s_q0[warp][k], s_q1[warp][k], s_q2[warp][k], s_pos[warp][k], s, g, half_w, half_h, v); if (f) id0 = s_id[warp][k]; k++; }
+      while (k < nh && !f) { f = bwd_entry<DEPTH>(slots + k, s, g, v); if (f) id0 = slots[k].id; k++; }
       if (!f) break;
       f = false;
-      while (k < nh && !f) { f = bwd_entry<DEPTH>(s_q0[warp][k], s_q1[warp][k], s_q2[warp][k], s_pos[warp][k], s, g, half_w, half_h, v + 10); if (f) id1 = s_id[warp][k]; k++; }
+      while (k < nh && !f) { f = bwd_entry<DEPTH>(slots + k, s, g, v + 10); if (f) id1 = slots[k].id; k++; }
       if (!f) {
 #pragma unroll
         for (int i = 10; i < 20; i++) v[i] = 0.f;
       }
       f = false;
-      while (k < nh && !f) { f = bwd_entry<DEPTH>(s_q0[warp][k], s_q1[warp][k], s_q2[warp][k], s_pos[warp][k], s, g, half_w, half_h, v + 20); if (f) id2 = s_id[warp][k]; k++; }
+      while (k < nh && !f) { f = bwd_entry<DEPTH>(slots + k, s, g, v + 20); if (f) id2 = slots[k].id; k++; }
       if (!f) {
 #pragma unroll
         for (int i = 20; i < 30; i++) v[i] = 0.f;
@@ -306,9 +323,10 @@ __global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const
       v[30] = 0.f; v[31] = 0.f;
       butterfly_step<16>(v, lane); butterfly_step<8>(v, lane); butterfly_step<4>(v, lane);
       butterfly_step<2>(v, lane); butterfly_step<1>(v, lane);
-      const int e = lane / 10, c = lane - 10 * e;
-      const uint32_t gid = e == 0 ? id0 : (e == 1 ? id1 : (e == 2 ? id2 : 0xffffffffu));
-      if (gid != 0xffffffffu && v[0] != 0.f) atomicAdd(grec + (size_t)gid * GREC_FLOATS + c, v[0]);
+      uint32_t gid = red_e == 0 ? id0 : id1;
+      gid = red_e == 2 ? id2 : gid;
+      gid = red_e > 2 ? 0xffffffffu : gid;
+      if (gid != 0xffffffffu && v[0] != 0.f) atomicAdd(grec_lane + (size_t)gid * GREC_FLOATS, v[0]);
     }
     __syncwarp();  // slot reads of this chunk are done before the next chunk overwrites them
   }
