@@ -49,11 +49,19 @@ __device__ __forceinline__ bool subtile_hit(const float4 q0, const TileGeom& g) 
   return (q0.x + q0.z >= g.X0) && (q0.x - q0.z <= g.X1) && (q0.y + q0.w >= g.Y0) && (q0.y - q0.w <= g.Y1);
 }
 
+// A compacted hit as a warp keeps it in its private shared-memory slots: everything one entry needs behind ONE base
+// address (the loop index is warp-uniform, so the loads are broadcasts with immediate offsets).
+struct __align__(16) HitSlot {
+  float4 q1;   // (A, B, C, opacity)
+  float4 q2;   // (r, g, b, zc)
+  float x, y;
+  uint32_t pos, id;
+};
+
 // -------------------------------------------------------------------------------------------------
 template <bool DEPTH, bool COUNT>
 __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs a) {
-  __shared__ float4 s_q0[WARPS][32], s_q1[WARPS][32], s_q2[WARPS][32];
-  __shared__ uint32_t s_pos[WARPS][32];
+  __shared__ HitSlot s_slot[WARPS][32];
   if (*a.overflow) return;
   const int tile = blockIdx.x, view = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -63,6 +71,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs 
   const Rec* __restrict__ vrec = a.rec + (size_t)view * a.N;
   const uint32_t* __restrict__ list = a.vals + range.x;
   const uint32_t len = range.y - range.x;
+  HitSlot* const slots = s_slot[warp];
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
   uint32_t last = 0, nblend = 0;
@@ -85,37 +94,35 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs 
       const uint32_t mask = __ballot_sync(0xffffffffu, hit);
       if (mask == 0) continue;
       if (hit) {
-        const int slot = __popc(mask & lt);
+        HitSlot* d = slots + __popc(mask & lt);
         const float4* r = reinterpret_cast<const float4*>(vrec + id);
-        s_q0[warp][slot] = q0; s_q1[warp][slot] = __ldg(r + 1); s_q2[warp][slot] = __ldg(r + 2);
-        s_pos[warp][slot] = base + lane + 1u;
+        d->q1 = __ldg(r + 1); d->q2 = __ldg(r + 2);
+        d->x = q0.x; d->y = q0.y; d->pos = base + lane + 1u; d->id = id;
       }
       __syncwarp();
       const int nh = __popc(mask);
       for (int k = 0; k < nh; k++) {
-        if (!done) {
-          const float4 h0 = s_q0[warp][k], h1 = s_q1[warp][k];
-          const float dx = __fsub_rn(h0.x, g.pfx), dy = __fsub_rn(h0.y, g.pfy);
-          const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
-          if (power <= 0.0f) {
-            const float alpha = fminf(ALPHA_MAX, __fmul_rn(h1.w, expf(power)));
-            if (alpha >= ALPHA_MIN) {
-              const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-              if (test_T < T_MIN) {
-                done = true;
-              } else {
-                const float4 h2 = s_q2[warp][k];
-                C0 = __fmaf_rn(__fmul_rn(h2.x, alpha), T, C0);
-                C1 = __fmaf_rn(__fmul_rn(h2.y, alpha), T, C1);
-                C2 = __fmaf_rn(__fmul_rn(h2.z, alpha), T, C2);
-                if (DEPTH) D = __fmaf_rn(__fmul_rn(h2.w, alpha), T, D);
-                T = test_T;
-                last = s_pos[warp][k];
-                if (COUNT) nblend++;
-              }
-            }
-          }
-        }
+        // one warp-uniform branch per hit (does ANY pixel blend it?), selects below it: a lane the entry does not
+        // reach adds exactly zero and keeps T / last
+        const HitSlot* h = slots + k;
+        const float4 h1 = h->q1;
+        const float dx = __fsub_rn(h->x, g.pfx), dy = __fsub_rn(h->y, g.pfy);
+        const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
+        const float alpha = fminf(ALPHA_MAX, __fmul_rn(h1.w, expf(power)));
+        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+        const bool reach = !done && power <= 0.0f && alpha >= ALPHA_MIN;
+        const bool live = reach && !(test_T < T_MIN);
+        done = done || (reach && !live);
+        if (!__any_sync(0xffffffffu, live)) continue;
+        const float4 h2 = h->q2;
+        const float a_eff = live ? alpha : 0.f;
+        C0 = __fmaf_rn(__fmul_rn(h2.x, a_eff), T, C0);
+        C1 = __fmaf_rn(__fmul_rn(h2.y, a_eff), T, C1);
+        C2 = __fmaf_rn(__fmul_rn(h2.z, a_eff), T, C2);
+        if (DEPTH) D = __fmaf_rn(__fmul_rn(h2.w, a_eff), T, D);
+        T = live ? test_T : T;
+        last = live ? h->pos : last;
+        if (COUNT) nblend += live ? 1u : 0u;
       }
       __syncwarp();  // this chunk's slot reads are done before the next chunk overwrites the slots
       if (__all_sync(0xffffffffu, done)) break;
@@ -171,15 +178,6 @@ struct PixState {
   uint32_t last_contributor;
 };
 
-// A compacted hit as the backward keeps it in the warp's shared-memory slots: everything one entry needs behind ONE
-// base address (the loop index is warp-uniform, so the loads are broadcasts with immediate offsets).
-struct __align__(16) BwdSlot {
-  float4 q1;   // (A, B, C, opacity)
-  float4 q2;   // (r, g, b, zc)
-  float x, y;
-  uint32_t pos, id;
-};
-
 __device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP; the argument is 1 - alpha in [0.01, 1]
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -193,7 +191,7 @@ __device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP; the arg
 // does not reach runs the same arithmetic with alpha = 0 (T, the weights and q come out unchanged / zero) and keeps
 // its recurrence state through selects.
 template <bool DEPTH>
-__device__ __forceinline__ bool bwd_entry(const BwdSlot* __restrict__ h, PixState<DEPTH>& s, const TileGeom& g, float* out) {
+__device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, PixState<DEPTH>& s, const TileGeom& g, float* out) {
   const float4 h1 = h->q1;
   const float dx = __fsub_rn(h->x, g.pfx), dy = __fsub_rn(h->y, g.pfy);
   const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
@@ -236,7 +234,7 @@ __device__ __forceinline__ bool bwd_entry(const BwdSlot* __restrict__ h, PixStat
 
 template <bool DEPTH, int MIN_CTAS>
 __global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const CompArgs a) {
-  __shared__ BwdSlot s_slot[WARPS][32];
+  __shared__ HitSlot s_slot[WARPS][32];
   if (*a.overflow) return;
   const int tile = blockIdx.x, view = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -276,7 +274,7 @@ __global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const
 
   // walk positions wmax-1 ... 0; lane l of a chunk starting at `top` holds position top-1-l, so that the
   // compacted slots ascend as the list is walked back to front
-  BwdSlot* const slots = s_slot[warp];
+  HitSlot* const slots = s_slot[warp];
   int top = (int)wmax;
   uint32_t id_cur = top - 1 - lane >= 0 ? __ldg(list + (top - 1 - lane)) : 0u;
   uint32_t id_nxt = top - 33 - lane >= 0 ? __ldg(list + (top - 33 - lane)) : 0u;
@@ -293,7 +291,7 @@ __global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const
     const uint32_t mask = __ballot_sync(0xffffffffu, hit);
     if (mask == 0) continue;
     if (hit) {
-      BwdSlot* d = slots + __popc(mask & lt);
+      HitSlot* d = slots + __popc(mask & lt);
       const float4* r = reinterpret_cast<const float4*>(vrec + id);
       d->q1 = __ldg(r + 1); d->q2 = __ldg(r + 2);
       d->x = q0.x; d->y = q0.y; d->pos = (uint32_t)pos; d->id = id;
