@@ -17,8 +17,8 @@
 namespace b200s {
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per tile
+constexpr int SORT_ITEMS = 12;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 3072 pairs per tile: 64 registers and 44 KB -> four CTAs per SM
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX = 256;
 // look-back words are 64-bit (2 flag bits + count) so that one call can sort up to 2^32 - 1 pairs
@@ -138,15 +138,15 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 
 constexpr int LOOKBACK_BATCH = 8;
 // dynamic shared memory of the pass kernel
-constexpr size_t SWEEP_SMEM = SORT_TILE * 8 + SORT_TILE * 4 + SORT_TILE * 4 + SORT_WARPS * RADIX * 4;
+constexpr size_t SWEEP_SMEM = SORT_TILE * 8 + SORT_TILE * 4 + SORT_WARPS * RADIX * 4;
 
 template <int RMODE>
-__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(sweep_smem);                              // [4096] keys in sorted order
-  uint32_t* s_vin = reinterpret_cast<uint32_t*>(sweep_smem + SORT_TILE * 8);               // [4096] values as they arrive
-  uint32_t* s_vout = s_vin + SORT_TILE;                                                    // [4096] values in sorted order
-  uint32_t(*s_wc)[RADIX] = reinterpret_cast<uint32_t(*)[RADIX]>(s_vout + SORT_TILE);       // [8][256]
+  uint32_t* s_vin = reinterpret_cast<uint32_t*>(sweep_smem + SORT_TILE * 8);               // values as they arrive, then (same
+  uint32_t* s_vout = s_vin;                                                                // storage) in sorted order
+  uint32_t(*s_wc)[RADIX] = reinterpret_cast<uint32_t(*)[RADIX]>(s_vin + SORT_TILE);        // [8][256]
   __shared__ uint32_t s_goff[RADIX];
   __shared__ uint32_t s_dstart[RADIX];
   __shared__ uint32_t s_scan[SORT_WARPS];
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const Pa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
 #pragma unroll
-  for (int w = 0; w < SORT_WARPS; w++) { s_wc[w][tid] = 0; if (RMODE >= 3) s_vout[w * RADIX + tid] = 0; }
+  for (int w = 0; w < SORT_WARPS; w++) s_wc[w][tid] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const unsigned long long base = (unsigned long long)tile * SORT_TILE;
@@ -192,44 +192,14 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const Pa
   uint32_t rank[SORT_ITEMS];
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t* wc = s_wc[warp];
-  uint32_t* mm = s_vout + warp * RADIX;  // RMODE 3: per-warp match masks (s_vout is idle until the very end)
-  if (RMODE == 4) {
-    // Two independent ranking chains per warp (items 0..7 against `wc`, items 8..15 against a second counter
-    // array parked in the idle s_vout region): the read-count / leader-update round trip through shared
-    // memory is the serial part of the loop, and two chains in flight halve it.  Chain A matches with ballots
-    // (ALU pipe), chain B with MATCH.ANY (ADU pipe).
-    uint32_t* wcB = s_vout + warp * RADIX;
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS / 2; i++) {
-      const uint32_t dA = (uint32_t)(key[i] >> a.shift) & 255u, dB = (uint32_t)(key[i + SORT_ITEMS / 2] >> a.shift) & 255u;
-      const uint32_t pB = match_digit<1>(dB);
-      const uint32_t pA = match_digit<0>(dA);
-      const uint32_t rA = wc[dA], rB = wcB[dB];
-      __syncwarp();
-      if (lane == (__ffs(pA) - 1)) wc[dA] = rA + __popc(pA);
-      if (lane == (__ffs(pB) - 1)) wcB[dB] = rB + __popc(pB);
-      __syncwarp();
-      rank[i] = rA + __popc(pA & lt);
-      rank[i + SORT_ITEMS / 2] = rB + __popc(pB & lt);
-    }
-    // chain A's items precede chain B's in tile order: B ranks shift by A's count of the same digit
-#pragma unroll
-    for (int i = SORT_ITEMS / 2; i < SORT_ITEMS; i++) rank[i] += wc[(uint32_t)(key[i] >> a.shift) & 255u];
-  } else
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const uint32_t d = (uint32_t)(key[i] >> a.shift) & 255u;
     uint32_t peers;
-    if (RMODE == 3) {  // lanes OR their bit into the digit's mask word: one shared atomic instead of eight votes
-      atomicOr(&mm[d], 1u << lane);
-      __syncwarp();
-      peers = mm[d];
-    } else {
-      peers = RMODE == 2 ? ((i & 1) ? match_digit<1>(d) : match_digit<0>(d)) : match_digit<(RMODE == 1 ? 1 : 0)>(d);
-    }
+    peers = RMODE == 2 ? ((i & 1) ? match_digit<1>(d) : match_digit<0>(d)) : match_digit<(RMODE == 1 ? 1 : 0)>(d);
     const uint32_t r = wc[d];
     __syncwarp();
-    if (lane == (__ffs(peers) - 1)) { wc[d] = r + __popc(peers); if (RMODE == 3) mm[d] = 0; }
+    if (lane == (__ffs(peers) - 1)) wc[d] = r + __popc(peers);
     __syncwarp();
     rank[i] = r + __popc(peers & lt);
   }
@@ -238,7 +208,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const Pa
   uint32_t run = 0;
 #pragma unroll
   for (int w = 0; w < SORT_WARPS; w++) {
-    const uint32_t t = s_wc[w][tid] + (RMODE == 4 ? s_vout[w * RADIX + tid] : 0u);
+    const uint32_t t = s_wc[w][tid];
     s_wc[w][tid] = run;
     run += t;
   }
@@ -295,10 +265,15 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(const Pa
   // values have landed by now; wait for this thread's copies, the barrier below makes all of them visible
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  // the sorted values take the place of the arrived ones: read this thread's, barrier, write by rank
+  uint32_t val[SORT_ITEMS];
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) val[i] = s_vin[wbase + i * 32];
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const uint32_t e = wbase + i * 32;
-    if (e < nvalid) s_vout[rank[i]] = s_vin[e];
+    if (e < nvalid) s_vout[rank[i]] = val[i];
   }
 #pragma unroll
   for (int j = 0; j < SORT_ITEMS; j++) {
@@ -380,8 +355,6 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
       if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
       if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
       if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
-      if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
-      if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
       sweep_configured = true;
     }
   }
@@ -396,9 +369,7 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     const int nblk = tiles - 1 > 0 ? tiles - 1 : 1;
     if (g_sort_knobs[1] == 0) onesweep_pass_kernel<0><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
     else if (g_sort_knobs[1] == 1) onesweep_pass_kernel<1><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
-    else if (g_sort_knobs[1] == 2) onesweep_pass_kernel<2><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
-    else if (g_sort_knobs[1] == 3) onesweep_pass_kernel<3><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
-    else onesweep_pass_kernel<4><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
+    else onesweep_pass_kernel<2><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
     count_launches(1);
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
