@@ -54,13 +54,32 @@ class _SyncGrads(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        # four in-place all-reduces (the tensors are fresh outputs of the rasterizer's backward): no flatten / split
-        # copies of the 160 B per Gaussian.  (torch's _coalescing_manager would make it one NCCL group call, but it
-        # gave erratic step times on the B200 box: 9.8 - 15 ms against a stable 9.8 ms.)
+        # in-place all-reduce of the fresh outputs of the rasterizer's backward: no flatten / split copies of the 160 B
+        # per Gaussian.  The rasterizer carves the four tensors out of one allocation, so it is ONE collective over
+        # 40 floats per Gaussian; tensors from elsewhere get one call each.  (torch's _coalescing_manager would also
+        # make it one NCCL group call, but it gave erratic step times on the B200 box: 9.8 - 15 ms against 9.8 ms.)
         grads = [g.contiguous() for g in grads]
-        for g in grads:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        flat = _flat_span(grads)
+        if flat is not None:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=ctx.group)   # one call over the rasterizer's flat gradient buffer
+        else:
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
         return (None, *grads)
+
+
+def _flat_span(tensors):
+    """The 1-D tensor that covers ``tensors`` exactly when they tile one contiguous stretch of a single storage without
+    gaps or overlaps (the rasterizer's backward allocates its four gradient tensors that way), else None."""
+    if len(tensors) < 2 or any(t.dtype != tensors[0].dtype or not t.is_contiguous() for t in tensors):
+        return None
+    st = tensors[0].untyped_storage()
+    if any(t.untyped_storage().data_ptr() != st.data_ptr() for t in tensors):
+        return None
+    spans = sorted((t.storage_offset(), t.storage_offset() + t.numel()) for t in tensors)
+    if any(a[1] != b[0] for a, b in zip(spans, spans[1:])):
+        return None
+    return torch.empty(0, dtype=tensors[0].dtype, device=tensors[0].device).set_(st, spans[0][0], (spans[-1][1] - spans[0][0],))
 
 
 def sync_gaussian_grads(gaussians: Gaussians, group: Optional[dist.ProcessGroup] = None) -> Gaussians:

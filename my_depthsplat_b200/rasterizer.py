@@ -293,10 +293,7 @@ class _Rasterize(torch.autograd.Function):
             call(_lib.GradIn(mc[0], mc[1], mc[2] if use_sh else None, None if use_sh else mc[2], mc[3], _ptr(d_m2d), 1, 0, 0, 0))
             reducer.end()
         else:
-            d_means = torch.empty_like(means)
-            d_covs = torch.empty_like(covs)
-            d_colors = torch.empty_like(colors)
-            d_op = torch.empty_like(opacities)
+            d_means, d_covs, d_colors, d_op = _grad_tensors(means, covs, colors, opacities)
             mk = lambda stages, c0, cn: _lib.GradIn(_ptr(d_means), _ptr(d_covs), _ptr(d_colors) if use_sh else None,
                                                     None if use_sh else _ptr(d_colors), _ptr(d_op), _ptr(d_m2d), 0, stages, c0, cn)
             if reducer is None:
@@ -318,6 +315,21 @@ class _Rasterize(torch.autograd.Function):
                 for w in works:
                     w.wait()
         return d_means, d_covs, d_colors, d_op, d_m2d, None, None, None, None, None, None
+
+
+def _grad_tensors(*like):
+    """Gradient tensors shaped like the inputs, carved back to back out of ONE allocation when every size keeps the next
+    one 16-byte aligned (it does whenever N is a multiple of 4): a cross-rank sum of the per-Gaussian gradients
+    (dist._SyncGrads) is then a single all-reduce over the flat buffer instead of one per tensor."""
+    sizes = [t.numel() for t in like]
+    if any(n % 4 for n in sizes[:-1]):
+        return tuple(torch.empty_like(t) for t in like)
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=like[0].device)
+    out, o = [], 0
+    for t, n in zip(like, sizes):
+        out.append(flat[o:o + n].view(t.shape))
+        o += n
+    return tuple(out)
 
 
 def rasterize(means: torch.Tensor, covariances: torch.Tensor, colors: torch.Tensor, opacities: torch.Tensor, views: ViewPack, *,

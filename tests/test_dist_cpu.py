@@ -57,7 +57,16 @@ def _worker(rank, world, port, result_dir):
         local = render_clip(OracleDecoder(), g, scene.extrinsics, scene.intrinsics, scene.near, scene.far, scene.image_shape, chunk_size=None)
         assert local.color.shape[1] == hi - lo and local.depth is None
         assert torch.equal(local.color, clip.color[:, lo:hi])
-        torch.save({"color": full.color, "depth": full.depth, "clip_color": clip.color, "clip_depth": clip.depth, "grads": [g.means.grad, g.covariances.grad, g.harmonics.grad, g.opacities.grad]},
+        # --- gradients carved out of one allocation (what the CUDA rasterizer's backward returns): one flat all-reduce
+        from my_depthsplat_b200.rasterizer import _grad_tensors
+        xs = [torch.zeros(s, requires_grad=True) for s in ((1, 8, 3), (1, 8, 3, 3), (1, 8, 3, 9), (1, 8))]
+        carved = _grad_tensors(*xs)
+        assert D._flat_span(list(carved)) is not None
+        for i, t in enumerate(carved):
+            t.fill_(float((rank + 1) * (i + 1)))
+        torch.autograd.backward(D._SyncGrads.apply(None, *xs), grad_tensors=list(carved))
+        flat_sums = [float(x.grad.min()) for x in xs] + [float(x.grad.max()) for x in xs]
+        torch.save({"color": full.color, "depth": full.depth, "flat_sums": flat_sums, "clip_color": clip.color, "clip_depth": clip.depth, "grads": [g.means.grad, g.covariances.grad, g.harmonics.grad, g.opacities.grad]},
                    Path(result_dir) / f"rank{rank}.pt")
     finally:
         dist.destroy_process_group()
@@ -90,6 +99,7 @@ def test_view_sharded_decoder_two_ranks(tmp_path):
     ((c * scene.grad_color).sum() + (d * scene.grad_depth).sum()).backward()
     for r in res:
         assert torch.equal(r["color"], c.detach()) and torch.equal(r["depth"], d.detach())  # gathered frames = 1-process frames
+        assert r["flat_sums"] == [3.0, 6.0, 9.0, 12.0] * 2  # (1 + 2) * (i + 1) on every element of tensor i
         assert torch.equal(r["clip_color"], c.detach()) and torch.equal(r["clip_depth"], d.detach())  # chunked clip too
         for got, ref in zip(r["grads"], (g.means.grad, g.covariances.grad, g.harmonics.grad, g.opacities.grad)):
             torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-6 * float(ref.abs().max()))  # sum order differs
