@@ -143,7 +143,7 @@ constexpr size_t SWEEP_SMEM = SORT_TILE * 8 + SORT_TILE * 4 + SORT_WARPS * RADIX
 template <int RMODE>
 __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(const PassArgs a) {
   extern __shared__ __align__(16) unsigned char sweep_smem[];
-  uint64_t* s_keys = reinterpret_cast<uint64_t*>(sweep_smem);                              // [4096] keys in sorted order
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(sweep_smem);                              // [SORT_TILE] keys in sorted order
   uint32_t* s_vin = reinterpret_cast<uint32_t*>(sweep_smem + SORT_TILE * 8);               // values as they arrive, then (same
   uint32_t* s_vout = s_vin;                                                                // storage) in sorted order
   uint32_t(*s_wc)[RADIX] = reinterpret_cast<uint32_t(*)[RADIX]>(s_vin + SORT_TILE);        // [8][256]

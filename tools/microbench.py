@@ -46,7 +46,7 @@ if __name__ == "__main__":
     if what == "sort":
         args = [int(a) for a in sys.argv[2:4]]
         for hv in (2,):
-            for rv in (0, 1, 2, 3, 4):
+            for rv in (0, 1, 2):
                 _lib.load().b200s_debug_set(0, hv); _lib.load().b200s_debug_set(1, rv)
                 print(f"hist variant {hv}, rank variant {rv}:", end=" ")
                 bench_sort(*args)
