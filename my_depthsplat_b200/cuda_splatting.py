@@ -67,6 +67,100 @@ def _depth_block(extrinsics_raw: Tensor, near_raw: Tensor, far_raw: Tensor):
     return w2c[:, 2, :].contiguous(), torch.stack([near_raw, far_raw], dim=-1).contiguous()
 
 
+def _camera_tensors(ext: Tensor, K: Tensor, near_f: Tensor, far_f: Tensor, want_depth: bool, scale_invariant: bool):
+    """Everything the kernels need per view, as a pure function of the cameras ([VV,4,4], [VV,3,3], [VV], [VV]): the
+    reference's lines :63-70 (scale-invariant normalisation of the camera side), :79-86 (field of view, projection and
+    view matrices) and :238-241 (row of the un-normalised world->camera matrix for the depth colour), same torch
+    operations in the same order.  -> (view, full, campos, tanfov, scale_pack | None, depth_affine | None,
+    depth_clamp | None)."""
+    depth_affine = depth_clamp = None
+    if want_depth:
+        depth_affine, depth_clamp = _depth_block(ext, near_f, far_f)
+    scale_pack = None
+    if scale_invariant:
+        scale = 1 / near_f
+        ext = ext.clone()
+        ext[..., :3, 3] = ext[..., :3, 3] * scale[:, None]
+        scale_pack = torch.stack([scale, scale ** 2], dim=-1).contiguous()
+        near_f = near_f * scale
+        far_f = far_f * scale
+    fov_x, fov_y = get_fov(K).unbind(dim=-1)
+    tan_fov_x, tan_fov_y = (0.5 * fov_x).tan(), (0.5 * fov_y).tan()
+    view, full, campos, tanfov = _camera_block(ext, near_f, far_f, fov_x, fov_y, tan_fov_x, tan_fov_y)
+    return view, full, campos, tanfov, scale_pack, depth_affine, depth_clamp
+
+
+# The camera block is ~60 tiny torch kernels: at 256x256 their launches cost as much host time as the whole
+# rasterizer.  They are a fixed sequence for a given number of views, so they are captured ONCE per
+# (device, views, flags) in a CUDA graph and replayed: same kernels, same arithmetic, one launch.
+use_camera_graph = True
+_camera_graphs: dict = {}
+_scene_index_cache: dict = {}
+
+
+class _CameraGraph:
+    def __init__(self, ext, K, near_f, far_f, want_depth, scale_invariant):
+        dev = ext.device
+        self.static_in = [t.detach().clone() for t in (ext, K, near_f, far_f)]
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside the capture: cuBLAS / cuSOLVER handles and workspaces
+            for _ in range(2):
+                _camera_tensors(*self.static_in, want_depth, scale_invariant)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            outs = _camera_tensors(*self.static_in, want_depth, scale_invariant)
+            self.shapes = [None if o is None else tuple(o.shape) for o in outs]
+            self.flat = torch.cat([o.reshape(-1) for o in outs if o is not None])
+
+    def __call__(self, ext, K, near_f, far_f):
+        for dst, src in zip(self.static_in, (ext, K, near_f, far_f)):
+            dst.copy_(src)
+        self.graph.replay()
+        flat = self.flat.clone()  # the static result is overwritten by the next replay; the views are saved for backward
+        outs, o = [], 0
+        for shp in self.shapes:
+            if shp is None:
+                outs.append(None)
+                continue
+            n = 1
+            for d in shp:
+                n *= d
+            outs.append(flat[o:o + n].view(shp))
+            o += n
+        return tuple(outs)
+
+
+def _camera_tensors_cached(ext, K, near_f, far_f, want_depth, scale_invariant):
+    eligible = (use_camera_graph and ext.is_cuda and not torch.cuda.is_current_stream_capturing()
+                and not (ext.requires_grad or K.requires_grad or near_f.requires_grad or far_f.requires_grad))
+    if not eligible:
+        return _camera_tensors(ext, K, near_f, far_f, want_depth, scale_invariant)
+    key = (ext.device, ext.shape[0], want_depth, scale_invariant)
+    g = _camera_graphs.get(key)
+    if g is None:
+        try:
+            g = _CameraGraph(ext, K, near_f, far_f, want_depth, scale_invariant)
+        except Exception as e:  # capture is an optimisation: fall back to the eager sequence, once and loudly
+            import warnings
+            warnings.warn(f"camera-block CUDA graph capture failed ({type(e).__name__}: {e}); running the torch ops eagerly")
+            g = False
+        _camera_graphs[key] = g
+    if g is False:
+        return _camera_tensors(ext, K, near_f, far_f, want_depth, scale_invariant)
+    return g(ext, K, near_f, far_f)
+
+
+def _scene_index(dev, B: int, V: int) -> Tensor:
+    key = (dev, B, V)
+    t = _scene_index_cache.get(key)
+    if t is None:
+        t = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(V)
+        _scene_index_cache[key] = t
+    return t
+
+
 def render_views(
     extrinsics: Tensor,            # [B,V,4,4] camera-to-world, OpenCV
     intrinsics: Tensor,            # [B,V,3,3] normalised
@@ -121,26 +215,12 @@ def _render_views_once(extrinsics, intrinsics, near, far, image_shape, backgroun
     K = intrinsics.reshape(B * V, 3, 3).to(torch.float32)
     near_f, far_f = near.reshape(B * V).to(torch.float32), far.reshape(B * V).to(torch.float32)
 
-    depth_affine = depth_clamp = None
-    if depth_mode is not None:
-        depth_affine, depth_clamp = _depth_block(ext, near_f, far_f)
-
-    scale_pack = None
-    if scale_invariant:
-        scale = 1 / near_f
-        ext = ext.clone()
-        ext[..., :3, 3] = ext[..., :3, 3] * scale[:, None]
-        scale_pack = torch.stack([scale, scale ** 2], dim=-1).contiguous()
-        near_f = near_f * scale
-        far_f = far_f * scale
-
-    fov_x, fov_y = get_fov(K).unbind(dim=-1)
-    tan_fov_x, tan_fov_y = (0.5 * fov_x).tan(), (0.5 * fov_y).tan()
-    view, full, campos, tanfov = _camera_block(ext, near_f, far_f, fov_x, fov_y, tan_fov_x, tan_fov_y)
+    view, full, campos, tanfov, scale_pack, depth_affine, depth_clamp = _camera_tensors_cached(
+        ext, K, near_f, far_f, depth_mode is not None, scale_invariant)
 
     bg = background_color.to(device=dev, dtype=torch.float32)
     bg = bg.expand(B, V, 3).reshape(B * V, 3).contiguous() if bg.dim() == 1 else bg.reshape(B * V, 3).contiguous()
-    scene_index = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(V)
+    scene_index = _scene_index(dev, B, V)
 
     pack = ViewPack(scene_index, view, full, campos, tanfov, bg, h, w, scale_pack, depth_mode, depth_affine, depth_clamp,
                     grad_reducer)

@@ -144,3 +144,29 @@ def test_huge_footprints_split_views_and_stay_correct():
         color, _ = _render(scene, gc)
     assert ((color.cpu() - ref).abs() > 1e-5).float().mean() <= 1e-3
     assert R.last_stats.num_pairs > 10 * gc.means.shape[1]  # most Gaussians cover a large part of the 24-tile image
+
+
+def test_camera_block_graph_replays_the_eager_sequence_bit_for_bit():
+    """The ~60 torch kernels of the camera block are captured once per (device, views, flags) in a CUDA graph
+    (cuda_splatting._camera_tensors_cached): same outputs as the eager sequence for every new set of cameras, and a
+    result handed out earlier is not overwritten by a later replay."""
+    from my_depthsplat_b200 import cuda_splatting as cs
+    outs = []
+    for seed, name in ((0, "small"), (1, "small"), (2, "small")):
+        sc = make_scene(name, v_tgt=3).to("cuda")
+        ext = sc.extrinsics.reshape(-1, 4, 4).clone()
+        ext[:, :3, 3] += 0.01 * seed
+        K, near, far = sc.intrinsics.reshape(-1, 3, 3), sc.near.reshape(-1) * (1 + 0.1 * seed), sc.far.reshape(-1)
+        for want_depth in (False, True):
+            eager = cs._camera_tensors(ext, K, near, far, want_depth, True)
+            graphed = cs._camera_tensors_cached(ext, K, near, far, want_depth, True)
+            assert cs._camera_graphs[(ext.device, ext.shape[0], want_depth, True)] is not False, "capture failed"
+            for a, b in zip(eager, graphed):
+                assert (a is None) == (b is None)
+                if a is not None:
+                    assert torch.equal(a, b)
+            outs.append((eager, graphed))
+    for eager, graphed in outs:  # earlier results survived the later replays
+        for a, b in zip(eager, graphed):
+            if a is not None:
+                assert torch.equal(a, b)
