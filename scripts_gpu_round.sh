@@ -20,7 +20,7 @@ while [ $# -gt 0 ]; do
       # same command line run plain first, directly before, no pipe
       NCU_CMD="python bench.py --steps 1 --warmup 3 --no-cpu"
       $NCU_CMD > gpurun_out/ncu_plain.log 2>&1 &&
-      ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 80 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
+      ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 130 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
       echo "ncu-list rc=$?" ;;
     ncu-full)
       shift; REGEX="$1"
