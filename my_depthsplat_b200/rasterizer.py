@@ -149,10 +149,6 @@ def release_scratch() -> None:
     _saved_pool.clear()
 
 
-class _Ctx:
-    pass
-
-
 def _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp: ViewPack):
     B, N = means.shape[0], means.shape[1]
     sc = _lib.Scene()
@@ -200,14 +196,11 @@ class _Rasterize(torch.autograd.Function):
         cap = min(cap, _PAIR_LIMIT)
         words = _status_ring.words
         retries = 0
-        import time as _t
-        _t0 = _t.perf_counter()
         while True:
             plan = _lib.plan(B, N, VV, H, W, cap)
             lease = _SavedLease(dev, plan.saved_bytes)
             saved = lease.tensor
             scratch = _scratch(dev, plan.scratch_bytes)
-            _t1 = _t.perf_counter()
             _lib.check(L.b200s_forward_bin(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(),
                                            C.byref(out), stream), "b200s_forward_bin")
             # stage A wrote the pair count straight into mapped host memory; the event marks its end, and the
@@ -216,11 +209,7 @@ class _Rasterize(torch.autograd.Function):
             ev.record()
             _lib.check(L.b200s_forward_render(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(),
                                               C.byref(out), stream), "b200s_forward_render")
-            _t2 = _t.perf_counter()
             ev.synchronize()
-            _t3 = _t.perf_counter()
-            if debug_keep == "timing":
-                print(f"    fwd host: alloc {1e3*(_t1-_t0):.2f} enqueue {1e3*(_t2-_t1):.2f} wait {1e3*(_t3-_t2):.2f} ms", flush=True)
             num_pairs = int(words[2 * slot])
             flags = int(words[2 * slot + 1])
             if not (flags >> 32):
