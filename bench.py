@@ -205,7 +205,8 @@ def run_ours(args):
     dataset_cfg = type("DatasetCfg", (), {"background_color": [0.0, 0.0, 0.0]})()
     decoder = get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), dataset_cfg).to(dev)
     # view sharding + ONE NCCL all-reduce of the flattened per-Gaussian gradients in the backward (identity at N=1)
-    sharded = ViewShardedDecoder(decoder, fused_reduce=(world > 1 and args.fused_reduce), overlap_reduce=(world > 1 and args.overlap_reduce))
+    sharded = ViewShardedDecoder(decoder, fused_reduce=(world > 1 and args.fused_reduce), overlap_reduce=(world > 1 and args.overlap_reduce),
+                                 nvls_reduce=(world > 1 and args.nvls_reduce))
     if getattr(sharded, "reducer", None) is not None and hasattr(sharded.reducer, "chunks") and os.environ.get("B200S_REDUCE_CHUNKS"):
         sharded.reducer.chunks = int(os.environ["B200S_REDUCE_CHUNKS"])
     gnames = ("means", "covariances", "harmonics", "opacities")
@@ -478,6 +479,9 @@ def main():
     ap.add_argument("--overlap-reduce", action="store_true",
                     help="N>1: projection backward in 2 Gaussian ranges, each followed by an async NCCL all-reduce (measured: no "
                          "consistent gain at N=2, 9.6-13 ms against a stable 9.85 ms for one all-reduce after the backward)")
+    ap.add_argument("--nvls-reduce", action="store_true",
+                    help="N>1: gradients written into symmetric memory and summed in place by the library's own two-shot NVLS "
+                         "kernel (multimem.ld_reduce + multimem.st) instead of the NCCL all-reduce")
     ap.add_argument("--fused-reduce", action="store_true",
                     help="N>1: sum the gradients inside the backward kernel over NVLS multicast (multimem.red) instead of one NCCL "
                          "all-reduce; measured SLOWER on B200 (one-shot multimem.red delivers every rank's data to every rank)")

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 5
+#define B200S_ABI_VERSION 6
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -213,6 +213,13 @@ void b200s_debug_set(int which, int value);
  * (cudaHostAlloc).  Under unified addressing the returned pointer is valid on host and device. */
 void* b200s_host_alloc(size_t bytes);
 void b200s_host_free(void* p);
+
+/* In-place sum over the `world` ranks of an NVSwitch domain of a SYMMETRIC buffer of n_floats floats (n_floats a
+ * multiple of 4, the buffer 16-byte aligned) given by its NVLS MULTICAST address: rank `rank` reduces its 1/world slice
+ * inside the switch (multimem.ld_reduce) and multicasts the sums back (multimem.st).  Replaces the NCCL all-reduce of
+ * the per-Gaussian gradients in view-sharded training (the reference is single-GPU: src/main.py:145-147).  The caller
+ * must order it on `stream` between two cross-rank barriers: all ranks' data complete before, all stores landed after. */
+int b200s_nvls_allreduce(void* multicast_ptr, unsigned long long n_floats, int rank, int world, void* stream);
 
 int b200s_abi_version(void);
 int b200s_last_cuda_error(void);       /* cudaError_t of the last failed launch on this thread */

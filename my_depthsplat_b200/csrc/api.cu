@@ -85,6 +85,13 @@ const char* b200s_build_info(void) {
   return "b200splat abi " B200S_STR(B200S_ABI_VERSION) " sm_100a nvcc " B200S_STR(__CUDACC_VER_MAJOR__) "." B200S_STR(__CUDACC_VER_MINOR__);
 }
 
+int b200s_nvls_allreduce(void* multicast_ptr, unsigned long long n_floats, int rank, int world, void* stream) {
+  if (!multicast_ptr || (n_floats & 3ull) || (reinterpret_cast<uintptr_t>(multicast_ptr) & 15) || world <= 0 || rank < 0 || rank >= world)
+    return B200S_EBADARG;
+  const cudaError_t e = b200s::launch_nvls_allreduce(static_cast<float*>(multicast_ptr), n_floats, rank, world, sm_count(), static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200S_OK : fail(e);
+}
+
 int b200s_plan(const B200sDims* d, B200sPlan* p) {
   if (!d || !p) return B200S_EBADARG;
   if (d->num_scenes <= 0 || d->num_gaussians <= 0 || d->num_views <= 0 || d->height <= 0 || d->width <= 0) return B200S_EBADARG;

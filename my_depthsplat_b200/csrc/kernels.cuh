@@ -33,6 +33,7 @@ struct CompArgs {
 // profiling hooks implemented in api.cu (no-ops unless b200s_profile_enable(1))
 void stage_mark(int stage, cudaStream_t stream);
 void count_launches(int n);
+cudaError_t launch_nvls_allreduce(float* multicast, unsigned long long n_floats, int rank, int world, int sm_count, cudaStream_t stream);
 extern int g_sort_knobs[4];
 
 cudaError_t launch_preprocess_bin(const B200sScene&, const B200sViews&, const B200sPlan&, char* saved, char* scratch, const B200sOut*,

@@ -159,6 +159,59 @@ class FusedGradReducer:
         self._cur.barrier(channel=1)
 
 
+class NvlsAllReducer:
+    """Cross-rank gradient sum WITHOUT NCCL: the backward kernel writes its four gradient tensors (ordinary stores)
+    into ONE buffer of torch symmetric memory, and the library's own two-shot NVLS kernel (``b200s_nvls_allreduce``,
+    csrc/collective.cu: ``multimem.ld_reduce`` + ``multimem.st``, 1/N of the buffer per rank) sums it in place between
+    two cross-rank barriers.  ``ROTATE`` buffers alternate: the tensors handed out by one backward stay valid until
+    ``ROTATE - 1`` further backward passes have run (their consumer -- the encoder's backward, an optimiser -- reads
+    them long before)."""
+
+    ROTATE = 3
+    in_place = True
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        self._bufs = {}
+        self._turn = 0
+        self.available = self.world > 1 and torch.cuda.is_available()
+
+    def begin(self, shapes, device):
+        """-> local gradient tensors (views of this rank's replica of the symmetric buffer)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        offs, o = [], 0
+        for n in sizes:
+            offs.append(o)
+            o += (n + 3) // 4 * 4
+        key = (o, device)
+        if key not in self._bufs:
+            ring = []
+            for _ in range(self.ROTATE):
+                t = symm_mem.empty(o, dtype=torch.float32, device=device)
+                h = symm_mem.rendezvous(t, self.group)
+                if not h.multicast_ptr:
+                    self.available = False
+                    raise RuntimeError("no NVLS multicast on this fabric")
+                t.zero_()  # the alignment gaps between the tensors are summed too
+                ring.append((t, h))
+            self._bufs[key] = ring
+        self._turn = (self._turn + 1) % self.ROTATE
+        self._cur = self._bufs[key][self._turn]
+        buf = self._cur[0]
+        return [buf[a:a + n].view(s) for a, n, s in zip(offs, sizes, shapes)]
+
+    def end(self):
+        from . import _lib
+        buf, h = self._cur
+        stream = torch.cuda.current_stream(buf.device).cuda_stream
+        h.barrier(channel=0)   # every rank's gradients are complete
+        _lib.check(_lib.load().b200s_nvls_allreduce(h.multicast_ptr, buf.numel(), self.rank, self.world, stream), "b200s_nvls_allreduce")
+        h.barrier(channel=1)   # every rank's multicast stores have landed
+
+
 class ChunkedAllReducer:
     """Sum of the per-Gaussian gradients over the ranks, OVERLAPPED with the kernel that produces them: the
     rasterizer runs its projection backward in ``chunks`` Gaussian ranges and hands each finished range to an
@@ -184,11 +237,16 @@ class ViewShardedDecoder(torch.nn.Module):
     (inference); otherwise the local slice (training: the loss is computed on the local views)."""
 
     def __init__(self, decoder: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, gather: bool = False,
-                 fused_reduce: bool = False, overlap_reduce: bool = False):
+                 fused_reduce: bool = False, overlap_reduce: bool = False, nvls_reduce: bool = False):
         super().__init__()
         self.decoder = decoder
         self.group = group
         self.gather = gather
+        # nvls_reduce: gradients land in symmetric memory and are summed in place by the library's NVLS kernel
+        if nvls_reduce and dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(decoder, "grad_reducer"):
+            self.reducer = NvlsAllReducer(group)
+            decoder.grad_reducer = self.reducer
+            return
         # overlap_reduce: chunked projection backward with one async NCCL all-reduce per chunk (ChunkedAllReducer)
         if overlap_reduce and not fused_reduce and dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(decoder, "grad_reducer"):
             self.reducer = ChunkedAllReducer(group)

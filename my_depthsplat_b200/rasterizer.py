@@ -276,7 +276,13 @@ class _Rasterize(torch.autograd.Function):
             _lib.check(L.b200s_backward(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(), C.byref(out),
                                         C.byref(gout), C.byref(gin), stream), "b200s_backward")
 
-        if reducer is not None and not getattr(reducer, "chunked", False):
+        if reducer is not None and getattr(reducer, "in_place", False):
+            # outputs are views of a symmetric-memory buffer; the reducer sums it over the ranks in place afterwards
+            d_means, d_covs, d_colors, d_op = reducer.begin([means.shape, covs.shape, colors.shape, opacities.shape], dev)
+            call(_lib.GradIn(_ptr(d_means), _ptr(d_covs), _ptr(d_colors) if use_sh else None, None if use_sh else _ptr(d_colors),
+                             _ptr(d_op), _ptr(d_m2d), 0, 0, 0, 0))
+            reducer.end()
+        elif reducer is not None and not getattr(reducer, "chunked", False):
             # outputs are NVLS multicast addresses: the kernel ADDS into every rank's (zeroed) replica
             (d_means, d_covs, d_colors, d_op), mc = reducer.begin([means.shape, covs.shape, colors.shape, opacities.shape], dev)
             call(_lib.GradIn(mc[0], mc[1], mc[2] if use_sh else None, None if use_sh else mc[2], mc[3], _ptr(d_m2d), 1, 0, 0, 0))

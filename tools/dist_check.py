@@ -1,6 +1,7 @@
 """N-GPU equivalence check (torchrun --nproc-per-node N tools/dist_check.py): view-sharded gradients, summed
-(a) by the fused NVLS reduce inside the backward kernel and (b) by a plain NCCL all-reduce, against the
-single-GPU gradients over all views."""
+(a) by the fused NVLS reduce inside the backward kernel, (b) by a plain NCCL all-reduce, (c) chunked / overlapped,
+(d) by the library's own two-shot NVLS all-reduce kernel on a symmetric buffer, against the single-GPU gradients over
+all views."""
 import os
 import sys
 from pathlib import Path
@@ -42,6 +43,8 @@ fused = [t.clone() for t in grads(fused_dec, (lo, hi))]
 fused2 = [t.clone() for t in grads(fused_dec, (lo, hi))]   # second call: the other symmetric buffer
 ovl_dec = ViewShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), overlap_reduce=True)
 ovl = grads(ovl_dec, (lo, hi))
+nvls_dec = ViewShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), nvls_reduce=True)
+nvls = [[t.clone() for t in grads(nvls_dec, (lo, hi))] for _ in range(4)]  # four calls: the buffer ring wraps around
 torch.cuda.synchronize()
 ok = True
 for nm, s, a, b, c, d in zip(("means", "covariances", "harmonics", "opacities"), single, nccl, fused, fused2, ovl):
@@ -49,6 +52,11 @@ for nm, s, a, b, c, d in zip(("means", "covariances", "harmonics", "opacities"),
     e_n, e_f, e_f2, e_o = (float((x - s).abs().max()) / scale for x in (a, b, c, d))
     print(f"rank {rank} {nm:12s} |nccl - single| {e_n:.2e}  |fused - single| {e_f:.2e}  |fused(2nd) - single| {e_f2:.2e}  |overlapped - single| {e_o:.2e}", flush=True)
     ok &= e_n < 2e-4 and e_f < 2e-4 and e_f2 < 2e-4 and e_o < 2e-4
+for k, nm in enumerate(("means", "covariances", "harmonics", "opacities")):
+    scale = float(single[k].abs().max())
+    errs = [float((nvls[j][k] - single[k]).abs().max()) / scale for j in range(4)]
+    print(f"rank {rank} {nm:12s} |NVLS kernel all-reduce - single| {max(errs):.2e} (4 calls)", flush=True)
+    ok &= max(errs) < 2e-4
 print(f"rank {rank} fused reducer active: {fused_dec.reducer is not None and fused_dec.reducer.available}  {'OK' if ok else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
