@@ -14,8 +14,9 @@ given the Gaussians, so the path shards without any data-path collective:
     views that the reference gets from the autograd of its per-view ``repeat``
     (decoder_splatting_cuda.py:53-56) therefore crosses ranks: ``sync_gaussian_grads`` is an identity
     in forward whose backward all-reduces the four gradient tensors in place (NCCL over NVLink 5 /
-    NVSwitch; 40 floats per Gaussian).  Two alternatives are implemented and measured, both opt-in because
-    neither beat the plain all-reduce on B200: ``FusedGradReducer`` (the backward kernel adds into NVLS
+    NVSwitch; 40 floats per Gaussian).  Three alternatives are implemented and measured, all opt-in:
+    ``NvlsAllReducer`` (gradients land in symmetric memory, the library's own two-shot NVLS kernel sums them in place:
+    slightly faster than NCCL at N=8, slower at N=2), ``FusedGradReducer`` (the backward kernel adds into NVLS
     multicast memory) and ``ChunkedAllReducer`` (projection backward in ranges, async all-reduce per range).
 """
 from __future__ import annotations
