@@ -197,10 +197,13 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(const Pa
     const uint32_t d = (uint32_t)(key[i] >> a.shift) & 255u;
     uint32_t peers;
     peers = RMODE == 2 ? ((i & 1) ? match_digit<1>(d) : match_digit<0>(d)) : match_digit<(RMODE == 1 ? 1 : 0)>(d);
-    const uint32_t r = wc[d];
-    __syncwarp();
-    if (lane == (__ffs(peers) - 1)) wc[d] = r + __popc(peers);
-    __syncwarp();
+    // the group's first lane bumps the warp's counter with one shared atomic and hands the old value to its group:
+    // no read / sync / write / sync round trip per item, and the atomics of successive items pipeline (same-address
+    // atomics of one warp execute in program order, so the ranking stays stable)
+    const int leader = __ffs(peers) - 1;
+    uint32_t r = 0;
+    if (lane == leader) r = atomicAdd(&wc[d], (uint32_t)__popc(peers));
+    r = __shfl_sync(0xffffffffu, r, leader);
     rank[i] = r + __popc(peers & lt);
   }
   __syncthreads();
@@ -275,16 +278,17 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(const Pa
     const uint32_t e = wbase + i * 32;
     if (e < nvalid) s_vout[rank[i]] = val[i];
   }
-#pragma unroll
-  for (int j = 0; j < SORT_ITEMS; j++) {
-    const uint32_t e = j * SORT_THREADS + tid;
-    if (e < nvalid) { const uint64_t k = s_keys[e]; a.keys_out[s_goff[(uint32_t)(k >> a.shift) & 255u] + e] = k; }
-  }
   __syncthreads();
+  // one walk over the sorted tile: the key is read once and gives the destination of both words
 #pragma unroll
   for (int j = 0; j < SORT_ITEMS; j++) {
     const uint32_t e = j * SORT_THREADS + tid;
-    if (e < nvalid) { const uint64_t k = s_keys[e]; a.vals_out[s_goff[(uint32_t)(k >> a.shift) & 255u] + e] = s_vout[e]; }
+    if (e < nvalid) {
+      const uint64_t k = s_keys[e];
+      const uint32_t dst = s_goff[(uint32_t)(k >> a.shift) & 255u] + e;
+      a.keys_out[dst] = k;
+      a.vals_out[dst] = s_vout[e];
+    }
   }
 }
 
