@@ -51,7 +51,10 @@ static_assert(sizeof(Rec) == 64, "record must be 64 bytes");
 constexpr uint32_t REC_FLAG_CLAMP_R = 1u, REC_FLAG_CLAMP_G = 2u, REC_FLAG_CLAMP_B = 4u;
 
 // ---- gradient record: 48 bytes per (view, Gaussian), accumulated by the compositing backward ----
-// (dL/dx, dL/dy, dL/dA, dL/dB, dL/dC, dL/dopacity, dL/dr, dL/dg, dL/db, dL/dzc, pad, pad)
+// the pixel moments of q = G * dL/dalpha and the colour gradients:
+// (S_x, S_y, S_xx, S_xy, S_yy, S_1, dL/dr, dL/dg, dL/db, dL/dzc, pad, pad), S_f = sum over pixels of q * f(dx, dy).
+// The projection backward turns them into dL/dmean2D = opacity * half_extent * (-A S_x - B S_y, -C S_y - B S_x),
+// dL/dconic = -opacity / 2 * (S_xx, S_xy, S_yy), dL/dopacity = S_1 (composite.cu, preprocess_bwd.cu).
 constexpr int GREC_FLOATS = 12;
 
 // per-view camera block staged in shared memory by the per-Gaussian kernels
