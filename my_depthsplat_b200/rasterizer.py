@@ -8,6 +8,11 @@ colors_precomp, opacities, cov3D_precomp), including the autograd of the per-vie
 (cuda_splatting.py:250-263).
 
 PyTorch here is plumbing only: device memory (caching allocator), the current stream, autograd.
+
+Threading: the call pattern of the reference is one Python thread per process driving the default stream, plus the
+autograd engine's thread for the backward.  The per-(device, stream) caches below (scratch buffer,
+workspace pool, capacity hints, host status ring) follow it: calls on different streams or devices are independent,
+two Python threads rendering on the SAME stream at the same time are not supported.
 """
 from __future__ import annotations
 
