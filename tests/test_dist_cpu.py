@@ -105,3 +105,42 @@ def test_view_sharded_decoder_two_ranks(tmp_path):
             torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-6 * float(ref.abs().max()))  # sum order differs
     for a, b in zip(res[0]["grads"], res[1]["grads"]):
         assert torch.equal(a, b)  # every rank holds the same reduced gradients
+
+
+def test_flat_span_recognises_only_gapless_tilings():
+    from my_depthsplat_b200.dist import _flat_span
+    from my_depthsplat_b200.rasterizer import _grad_tensors
+    like = [torch.zeros(2, 8, 3), torch.zeros(2, 8, 3, 3), torch.zeros(2, 8, 3, 9), torch.zeros(2, 8)]
+    carved = _grad_tensors(*like)
+    flat = _flat_span(list(carved))
+    assert flat is not None and flat.numel() == sum(t.numel() for t in like) and flat.data_ptr() == carved[0].data_ptr()
+    assert [t.shape for t in carved] == [t.shape for t in like]
+    flat.fill_(1.5)
+    assert all(float(t.min()) == 1.5 for t in carved)
+    # sizes that would misalign the next tensor fall back to separate allocations -> no flat span
+    odd = _grad_tensors(torch.zeros(1, 7, 3), torch.zeros(1, 7, 3, 3), torch.zeros(1, 7, 3, 9), torch.zeros(1, 7))
+    assert _flat_span(list(odd)) is None
+    # unrelated tensors, sub-ranges (gaps) and mixed dtypes are not spans
+    assert _flat_span([torch.zeros(4), torch.zeros(4)]) is None
+    assert _flat_span([carved[0][:, :4], carved[1][:, :4]]) is None
+    assert _flat_span([carved[0], carved[1].double()]) is None
+    assert _flat_span([carved[0]]) is None
+
+
+def test_render_clip_rejects_host_streaming_without_cuda_and_with_gather():
+    from my_depthsplat_b200.scenes import make_scene
+    from my_depthsplat_b200.types import DecoderOutput
+    from my_depthsplat_b200.video import render_clip
+    scene = make_scene("tiny")
+
+    class Dummy(torch.nn.Module):
+        def forward(self, g, e, k, n, f, shape, depth_mode=None):
+            return DecoderOutput(torch.zeros(e.shape[0], e.shape[1], 3, *shape), None)
+
+    args = (Dummy(), scene.gaussians, scene.extrinsics, scene.intrinsics, scene.near, scene.far, scene.image_shape)
+    out = render_clip(*args, chunk_size=1)
+    assert out.color.shape == (1, scene.extrinsics.shape[1], 3, *scene.image_shape) and out.depth is None
+    with pytest.raises(ValueError):
+        render_clip(*args, to_host=True)             # CPU tensors: there is no CPU path to stream from
+    with pytest.raises(ValueError):
+        render_clip(*args, to_host=True, gather=True)
