@@ -133,7 +133,8 @@ class _CameraGraph:
 
 
 def _camera_tensors_cached(ext, K, near_f, far_f, want_depth, scale_invariant):
-    eligible = (use_camera_graph and ext.is_cuda and not torch.cuda.is_current_stream_capturing()
+    eligible = (use_camera_graph and ext.is_cuda and ext.device.index == torch.cuda.current_device()
+                and not torch.cuda.is_current_stream_capturing()
                 and not (ext.requires_grad or K.requires_grad or near_f.requires_grad or far_f.requires_grad))
     if not eligible:
         return _camera_tensors(ext, K, near_f, far_f, want_depth, scale_invariant)
