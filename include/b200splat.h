@@ -206,7 +206,8 @@ int b200s_profile_read(float* ms_by_stage);
 long long b200s_kernel_launches(void);
 
 /* Tuning knobs for A/B measurements (not part of the stable contract): which 0 = digit-histogram variant
- * (0 ballots, 1 MATCH.ANY, 2 shared atomics), which 1 = ranking variant (0 ballots, 1 MATCH.ANY, 2 alternating). */
+ * (0 ballots, 1 MATCH.ANY, 2 shared atomics), which 1 = ranking variant (0 ballots, 1 MATCH.ANY, 2 alternating), which 2 = compositing-backward CTA shape (2: one
+ * eight-warp CTA per tile instead of two four-warp ones). */
 void b200s_debug_set(int which, int value);
 
 /* Host-memory utility (not on the data path): mapped, portable pinned memory that kernels can write

@@ -1,6 +1,8 @@
 // composite.cu -- 16x16-tile alpha compositing, forward and backward.
 //
-// One CTA of 256 threads per (view, tile); thread = pixel; each WARP owns an 8x4-pixel sub-tile and
+// One CTA of 256 threads per (view, tile) in the forward, two CTAs of 128 threads per (view, tile) in the backward
+// (smaller scheduling units: 28 instead of 24 resident warps at its register count); thread = pixel; each WARP owns an
+// 8x4-pixel sub-tile and
 // walks the tile's depth-sorted list ON ITS OWN -- there is no block-wide staging and no
 // __syncthreads in the list loop, so a warp whose pixels saturate early (or whose sub-tile few
 // Gaussians touch) never waits for the other seven.  Per 32 list entries a warp
@@ -33,8 +35,9 @@ struct TileGeom {
   bool inside;
   float pfx, pfy, X0, X1, Y0, Y1;
 };
-__device__ __forceinline__ TileGeom tile_geom(int tile, int grid_x, int H, int W) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// `warp` = which of the tile's eight 8x4 sub-tiles this warp owns
+__device__ __forceinline__ TileGeom tile_geom(int tile, int grid_x, int H, int W, int warp) {
+  const int lane = threadIdx.x & 31;
   const int tx = tile % grid_x, ty = tile / grid_x;
   const int x0 = tx * TILE_X + (warp & 1) * 8, y0 = ty * TILE_Y + (warp >> 1) * 4;
   TileGeom g;
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   const uint2 range = a.ranges[((uint32_t)view << a.tile_bits) | (uint32_t)tile];
-  const TileGeom g = tile_geom(tile, a.grid_x, a.H, a.W);
+  const TileGeom g = tile_geom(tile, a.grid_x, a.H, a.W, warp);
   const Rec* __restrict__ vrec = a.rec + (size_t)view * a.N;
   const uint32_t* __restrict__ list = a.vals + range.x;
   const uint32_t len = range.y - range.x;
@@ -234,16 +237,20 @@ __device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, PixStat
   return true;
 }
 
-template <bool DEPTH, int MIN_CTAS>
-__global__ void __launch_bounds__(TILE_PIX, MIN_CTAS) composite_bwd_kernel(const CompArgs a) {
-  __shared__ HitSlot s_slot[WARPS][32];
+// CTA_WARPS = 8: one CTA per tile; 4: two CTAs of four warps per tile (smaller scheduling units: MIN_CTAS of them fit
+// where the register file holds fewer whole tiles)
+template <bool DEPTH, int CTA_WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel(const CompArgs a) {
+  __shared__ HitSlot s_slot[CTA_WARPS][32];
   if (*a.overflow) return;
-  const int tile = blockIdx.x, view = blockIdx.y;
+  constexpr int PER_TILE = 8 / CTA_WARPS;  // CTAs per tile
+  const int tile = blockIdx.x / PER_TILE, view = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wsub = (int)(blockIdx.x % PER_TILE) * CTA_WARPS + warp;
   const uint32_t lt = (1u << lane) - 1u;
   const uint2 range = a.ranges[((uint32_t)view << a.tile_bits) | (uint32_t)tile];
   if (range.y == range.x) return;
-  const TileGeom g = tile_geom(tile, a.grid_x, a.H, a.W);
+  const TileGeom g = tile_geom(tile, a.grid_x, a.H, a.W, wsub);
   const Rec* __restrict__ vrec = a.rec + (size_t)view * a.N;
   const uint32_t* __restrict__ list = a.vals + range.x;
   const size_t HW = (size_t)a.H * a.W;
@@ -347,9 +354,18 @@ cudaError_t launch_composite_bwd(const CompArgs& a, int tiles, int views, bool d
   dim3 grid(tiles, views);
   stage_mark(B200S_STAGE_COMP_BWD, stream);
   count_launches(1);
-  // three CTAs per SM (80 registers): four (64 registers, 32 B of spills) measured 3.31 ms against 2.91 ms
-  if (depth) composite_bwd_kernel<true, 3><<<grid, TILE_PIX, 0, stream>>>(a);
-  else composite_bwd_kernel<false, 3><<<grid, TILE_PIX, 0, stream>>>(a);
+  // Two CTAs of four warps per tile, seven per SM (72 registers, 28 warps): 2.39 ms against 2.43 ms for one eight-warp
+  // CTA per tile at three per SM (76 registers, 24 warps); four two-warp CTAs per tile measure the same as two four-warp
+  // ones; capping the eight-warp kernel at 64 registers for four per SM spills and is slower (2.71 ms).
+  // b200s_debug_set(2, 2) selects the eight-warp shape for A/B runs.
+  if (g_sort_knobs[2] == 2) {
+    if (depth) composite_bwd_kernel<true, 8, 3><<<grid, TILE_PIX, 0, stream>>>(a);
+    else composite_bwd_kernel<false, 8, 3><<<grid, TILE_PIX, 0, stream>>>(a);
+  } else {
+    dim3 g2(tiles * 2, views);
+    if (depth) composite_bwd_kernel<true, 4, 7><<<g2, 128, 0, stream>>>(a);
+    else composite_bwd_kernel<false, 4, 7><<<g2, 128, 0, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 
