@@ -18,15 +18,15 @@ while [ $# -gt 0 ]; do
       python -m pytest tests/test_gpu_baseline.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/baseline_tests.log; echo "pytest rc=$?" >> gpurun_out/baseline_tests.log; tail -15 gpurun_out/baseline_tests.log ;;
     ncu-list)
       # same command line run plain first, directly before, no pipe
-      NCU_CMD="python bench.py --steps 1 --warmup 3 --no-cpu"
+      NCU_CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-gpu-baseline"
       $NCU_CMD > gpurun_out/ncu_plain.log 2>&1 &&
       ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 130 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_launches.log 2>&1
       echo "ncu-list rc=$?" ;;
     ncu-full)
       shift; REGEX="$1"
-      NCU_CMD="python bench.py --steps 1 --warmup 3 --no-cpu"
+      NCU_CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-gpu-baseline"
       $NCU_CMD > gpurun_out/ncu_plain.log 2>&1 &&
-      ncu --set full --clock-control none --import-source on -k regex:"$REGEX" -s 9 -c 6 -f -o gpurun_out/prof $NCU_CMD > gpurun_out/ncu_full.log 2>&1
+      ncu --set full --clock-control none --import-source on -k regex:"$REGEX" -s ${NCU_SKIP:-9} -c ${NCU_COUNT:-6} -f -o gpurun_out/prof $NCU_CMD > gpurun_out/ncu_full.log 2>&1
       echo "ncu-full rc=$?" ;;
   esac
   shift
