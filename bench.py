@@ -188,25 +188,35 @@ def run_ours(args):
     L = _lib.load()
     cfg = CONFIGS[args.config]
     V = args.views or cfg.v_tgt
-    scene_cpu = make_scene(cfg, v_tgt=V * world)  # same seed on every rank -> identical (replicated) Gaussians
+    by_scene = args.shard == "scenes"
+    if by_scene:
+        # BASELINE config 4: the scenes of the batch are split over the ranks (args.scenes per GPU, all V views each);
+        # every rank owns its scenes' Gaussians, so the rendering path needs no collective at all
+        scene_cpu = make_scene(cfg, batch=args.scenes * world, v_tgt=V)
+        bs, vs = slice(rank * args.scenes, (rank + 1) * args.scenes), slice(None)
+    else:
+        scene_cpu = make_scene(cfg, v_tgt=V * world)  # same seed on every rank -> identical (replicated) Gaussians
+        bs, vs = slice(None), slice(rank * V, (rank + 1) * V)  # this rank's shard of the target views
     H, W = scene_cpu.image_shape
     N = scene_cpu.gaussians.means.shape[1]
-    vs = slice(rank * V, (rank + 1) * V)  # this rank's shard of the target views
+    g_ = scene_cpu.gaussians
     host = {
-        "means": scene_cpu.gaussians.means, "covariances": scene_cpu.gaussians.covariances,
-        "harmonics": scene_cpu.gaussians.harmonics, "opacities": scene_cpu.gaussians.opacities,
-        # cameras of ALL world*V target views (a few hundred bytes); my_depthsplat_b200.dist slices this rank's views
-        "extrinsics": scene_cpu.extrinsics.contiguous(), "intrinsics": scene_cpu.intrinsics.contiguous(),
-        "near": scene_cpu.near.contiguous(), "far": scene_cpu.far.contiguous(),
-        "grad_color": scene_cpu.grad_color[:, vs].contiguous(),
+        "means": g_.means[bs].contiguous(), "covariances": g_.covariances[bs].contiguous(),
+        "harmonics": g_.harmonics[bs].contiguous(), "opacities": g_.opacities[bs].contiguous(),
+        # view sharding: cameras of ALL world*V target views (a few hundred bytes); my_depthsplat_b200.dist slices this rank's
+        "extrinsics": scene_cpu.extrinsics[bs].contiguous(), "intrinsics": scene_cpu.intrinsics[bs].contiguous(),
+        "near": scene_cpu.near[bs].contiguous(), "far": scene_cpu.far[bs].contiguous(),
+        "grad_color": scene_cpu.grad_color[bs, vs].contiguous(),
     }
+    B_local = host["means"].shape[0]
     host = {k: v.pin_memory() for k, v in host.items()}
     devt = {k: v.to(dev) for k, v in host.items()}
     dataset_cfg = type("DatasetCfg", (), {"background_color": [0.0, 0.0, 0.0]})()
     decoder = get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), dataset_cfg).to(dev)
     # view sharding + ONE NCCL all-reduce of the flattened per-Gaussian gradients in the backward (identity at N=1)
-    sharded = ViewShardedDecoder(decoder, fused_reduce=(world > 1 and args.fused_reduce), overlap_reduce=(world > 1 and args.overlap_reduce),
-                                 nvls_reduce=(world > 1 and args.nvls_reduce))
+    sharded = decoder if by_scene else ViewShardedDecoder(
+        decoder, fused_reduce=(world > 1 and args.fused_reduce), overlap_reduce=(world > 1 and args.overlap_reduce),
+        nvls_reduce=(world > 1 and args.nvls_reduce))
     if getattr(sharded, "reducer", None) is not None and hasattr(sharded.reducer, "chunks") and os.environ.get("B200S_REDUCE_CHUNKS"):
         sharded.reducer.chunks = int(os.environ["B200S_REDUCE_CHUNKS"])
     gnames = ("means", "covariances", "harmonics", "opacities")
@@ -302,7 +312,7 @@ def run_ours(args):
     W_ = max(args.warmup, 3)
     ms, launches, clocks = timed(lambda: step(devt), args.steps, W_)
     ms_step = ms / args.steps
-    pix_step = world * V * H * W
+    pix_step = world * B_local * V * H * W
     value = pix_step / (ms_step * 1e-3) / 1e6
 
     def e2e_finish():
@@ -345,24 +355,25 @@ def run_ours(args):
     # ---- work counters of one forward (pairs, visible, tested, blended) --------------------------------
     from my_depthsplat_b200.cuda_splatting import render_views
     with torch.no_grad():
-        render_views(*(shard_views(devt[k], world, rank) for k in ("extrinsics", "intrinsics", "near", "far")), (H, W), decoder.background_color,
+        render_views(*((devt[k] if by_scene else shard_views(devt[k], world, rank)) for k in ("extrinsics", "intrinsics", "near", "far")), (H, W), decoder.background_color,
                      devt["means"], devt["covariances"], devt["harmonics"], devt["opacities"], count_work=True)
     st = R.last_stats
-    plan = _lib.plan(1, N, V, H, W, max(st.num_pairs, 1))
+    plan = _lib.plan(B_local, N, B_local * V, H, W, max(st.num_pairs, 1))
 
     hbm_peak, sm_max, peak_src = _peaks()
     sm_mhz = clocks["sm_mhz"] or sm_max
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the clock seen under load
-    Rn, Nv, P = st.num_pairs, st.num_visible, V * H * W
+    Rn, Nv, P = st.num_pairs, st.num_visible, B_local * V * H * W
+    NB = N * B_local  # Gaussians of all scenes of this rank's call
     alg = {  # algorithmic bytes / flops per launch
-        "pre_bin": ("hbm", 148.0 * N * V + 64.0 * N * V + 12.0 * Rn),
+        "pre_bin": ("hbm", 148.0 * NB * V + 64.0 * NB * V + 12.0 * Rn),
         "sort_hist": ("hbm", 8.0 * Rn),
         "sort_passes": ("hbm", 24.0 * Rn * plan.sort_passes),
         "ranges": ("hbm", 8.0 * Rn + 8.0 * plan.bins),
         "comp_fwd": ("fp32", 15.0 * st.tested + 11.0 * st.blended),
         "comp_bwd": ("fp32", 15.0 * st.tested + 63.0 * st.blended),
-        "pre_bwd": ("hbm", 296.0 * N + 64.0 * N * V),
-        "grad_zero": ("hbm", 48.0 * N * V),
+        "pre_bwd": ("hbm", 296.0 * NB + 64.0 * NB * V),
+        "grad_zero": ("hbm", 48.0 * NB * V),
     }
     stage_report = {}
     for k, ms_k in stages_ms.items():
@@ -444,7 +455,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": _workload_name(cfg, scene_cpu, V), "views_per_gpu": V, "gaussians": N, "height": H, "width": W,
                        "l2": "inputs larger than L2 (Gaussians 472 MB + 64 B records per view)" if N * 160 > 126e6 else "inputs fit L2",
-                       "parallelism": f"view-sharded x{world}, Gaussians replicated" + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
+                       "parallelism": (f"scene-sharded x{world}: {B_local} scene(s) per GPU, no collective on the rendering path") if by_scene else f"view-sharded x{world}, Gaussians replicated" + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
                                         else (", NCCL all-reduce of per-Gaussian grads" + (" in 2 chunks overlapped with the projection backward" if args.overlap_reduce else ""))) if world > 1 else "")},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_step_e, 4), "pinned_copy_bandwidth": pcie, "allocator_events": alloc_events,
@@ -474,6 +485,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2T")
     ap.add_argument("--views", type=int, default=0, help="target views per GPU (default: the config's)")
+    ap.add_argument("--shard", default="views", choices=["views", "scenes"],
+                    help="N>1: split the target views of replicated scenes (default; gradients all-reduced) or the scenes of the "
+                         "batch (config 4: no collective on this path)")
+    ap.add_argument("--scenes", type=int, default=1, help="--shard scenes: scenes per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the upstream-style GPU comparator leg")
     ap.add_argument("--overlap-reduce", action="store_true",
