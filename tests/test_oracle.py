@@ -57,6 +57,32 @@ def test_oracle_matches_dense_float64(name, view):
         assert err.max() <= 2e-4 * scale, (key, err.max(), scale)
 
 
+@pytest.mark.parametrize("degree", [0, 1, 3])
+def test_oracle_sh_degrees_match_dense_float64(degree):
+    """The SH evaluation and its hand-derived backward (view-direction chain included) for the degrees the default
+    configs do not use: 1, 4 and 16 coefficients per channel."""
+    from my_depthsplat_b200.scenes import SceneConfig
+    sc = make_scene(SceneConfig(f"deg{degree}", 300 + degree, 2, 24, 32, sh_degree=degree))
+    inp = per_view_extension_inputs(sc, 0, 1)
+    st = so.forward_view(**inp)
+    assert (st.radii > 0).sum() > 0
+    kw, lv = _dense_inputs(inp)
+    img = dt.render_view(radii=torch.tensor(st.radii), **kw, **lv)
+    d = np.abs(img.detach().numpy() - st.color)
+    assert (d > 2e-5).mean() < 2e-3 and np.median(d) < 1e-6, d.max()
+    g = torch.randn(img.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    (img * g).sum().backward()
+    gr = so.backward_view(st, g.numpy().astype(np.float32))
+    hom = np.concatenate([inp["means3D"], np.ones((len(inp["means3D"]), 1), np.float32)], 1) @ inp["viewmatrix"].reshape(4, 4)
+    clamped = (np.abs(hom[:, 0] / hom[:, 2]) > 1.3 * inp["tanfovx"]) | (np.abs(hom[:, 1] / hom[:, 2]) > 1.3 * inp["tanfovy"])
+    for key, leaf in (("means3D", "means3D"), ("cov3D", "cov3D"), ("sh", "shs"), ("opacity", "opacities")):
+        ref = lv[leaf].grad.numpy()
+        err = np.abs(gr[key] - ref)
+        if key == "means3D":
+            err = err[~clamped]
+        assert err.max() <= 2e-4 * np.abs(ref).max(), (key, err.max(), np.abs(ref).max())
+
+
 def test_oracle_precomputed_colors_and_background():
     sc = make_scene("tiny")
     inp = per_view_extension_inputs(sc, 0, 0)
