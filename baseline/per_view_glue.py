@@ -92,6 +92,47 @@ def render_depth_cuda(ext, extrinsics, intrinsics, near, far, image_shape, gauss
     return result.mean(dim=1)
 
 
+def render_cuda_orthographic(ext, extrinsics, width, height, near, far, image_shape, background_color, gaussian_means,
+                             gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, fov_degrees=0.1, use_sh=True):
+    """cuda_splatting.py:129-219 of the reference: a fake orthographic camera (tiny field of view, camera moved back so that
+    the near plane keeps the requested width), then the same per-view loop; no scale-invariant normalisation.  The reference
+    hands the whole ``tan_fov_y`` tensor to every view's settings (it is only ever called with one view); here view i gets
+    element i, which is the same thing for one view."""
+    b = extrinsics.shape[0]
+    h, w = image_shape
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    n = gaussian_sh_coefficients.shape[-1]
+    degree = isqrt(n) - 1
+    shs = gaussian_sh_coefficients.permute(0, 1, 3, 2).contiguous()
+    fov_x = torch.tensor(fov_degrees, device=extrinsics.device).deg2rad()
+    tan_fov_x = (0.5 * fov_x).tan()
+    distance_to_near = (0.5 * width) / tan_fov_x
+    tan_fov_y = 0.5 * height / distance_to_near
+    fov_y = (2 * tan_fov_y).atan()
+    near = near + distance_to_near
+    far = far + distance_to_near
+    move_back = torch.eye(4, dtype=torch.float32, device=extrinsics.device)
+    move_back[2, 3] = -distance_to_near
+    extrinsics = extrinsics @ move_back
+    projection_matrix = get_projection_matrix(near, far, fov_x.expand(b), fov_y).transpose(1, 2)
+    view_matrix = extrinsics.inverse().transpose(1, 2)
+    full_projection = view_matrix @ projection_matrix
+    images = []
+    for i in range(b):
+        mean_gradients = torch.zeros_like(gaussian_means[i], requires_grad=True)
+        settings = ext.GaussianRasterizationSettings(
+            image_height=h, image_width=w, tanfovx=tan_fov_x, tanfovy=tan_fov_y[i], bg=background_color[i], scale_modifier=1.0,
+            viewmatrix=view_matrix[i], projmatrix=full_projection[i], sh_degree=degree, campos=extrinsics[i, :3, 3],
+            prefiltered=False, debug=False)
+        row, col = torch.triu_indices(3, 3)
+        image, _radii = ext.GaussianRasterizer(settings)(
+            means3D=gaussian_means[i], means2D=mean_gradients, shs=shs[i] if use_sh else None,
+            colors_precomp=None if use_sh else shs[i, :, 0, :], opacities=gaussian_opacities[i, ..., None],
+            cov3D_precomp=gaussian_covariances[i, :, row, col])
+        images.append(image)
+    return torch.stack(images)
+
+
 def _per_view(t, v):
     """[b, ...] -> [(b v), ...]: a materialised copy per view, like einops.repeat in the reference."""
     return t.repeat_interleave(v, dim=0)

@@ -112,25 +112,36 @@ def test_background_and_transparent_gaussians():
 
 
 def test_orthographic_variant_matches_the_oracle():
+    """render_cuda_orthographic (cuda_splatting.py:129-219): colour and gradients against the reference's orthographic
+    glue restated over the CPU oracle (baseline/per_view_glue.py; tests/test_reference_glue.py pins that restatement to
+    the unmodified reference file where /root/reference exists).  One view per call, as in the reference (its
+    ``move_back[2, 3] = -distance_to_near`` only accepts one)."""
+    from baseline import per_view_glue
     from my_depthsplat_b200 import cuda_splatting as cs
     from oracle import ext_compat
-    from helpers import have_reference, load_reference_cuda_splatting
-    scene = make_scene("tiny")
+    scene = make_scene("small")  # B = 2
     g = scene.gaussians
-    b = 1
-    ext = scene.extrinsics[0, :1]
-    width, height = torch.tensor([3.0]), torch.tensor([2.0])
-    near, far = torch.tensor([0.0]), torch.tensor([20.0])
-    args = lambda dev: (ext.to(dev), width.to(dev), height.to(dev), near.to(dev), far.to(dev), (32, 48), torch.zeros(b, 3, device=dev),
-                        g.means[:1].to(dev), g.covariances[:1].to(dev), g.harmonics[:1].to(dev), g.opacities[:1].to(dev))
-    with torch.no_grad():
-        mine = cs.render_cuda_orthographic(*args("cuda"))
-    assert mine.shape == (1, 3, 32, 48)
-    if have_reference():
-        ref_cs = load_reference_cuda_splatting(ext_compat)
-        with torch.no_grad():
-            ref = ref_cs.render_cuda_orthographic(*args("cpu"))
-        assert ((mine.cpu() - ref).abs() > 1e-5).float().mean() <= 2e-3
+    for b, view in ((1, 0), (1, 2)):
+        ext = scene.extrinsics[:b, view]
+        width, height = torch.tensor([3.0, 2.5][:b]), torch.tensor([2.0, 2.2][:b])
+        near, far = torch.zeros(b), torch.full((b,), 20.0)
+        bg = torch.tensor([[0.1, 0.2, 0.3], [0.0, 0.0, 0.0]])[:b]
+        ref_g = Gaussians(*(t[:b].clone().requires_grad_() for t in (g.means, g.covariances, g.harmonics, g.opacities)))
+        ref = per_view_glue.render_cuda_orthographic(ext_compat, ext, width, height, near, far, (32, 48), bg, ref_g.means,
+                                                     ref_g.covariances, ref_g.harmonics, ref_g.opacities)
+        w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6)) / ref[0].numel()
+        (ref * w).sum().backward()
+        mine_g = _cuda(Gaussians(g.means[:b], g.covariances[:b], g.harmonics[:b], g.opacities[:b]), grad=True)
+        mine = cs.render_cuda_orthographic(ext.cuda(), width.cuda(), height.cuda(), near.cuda(), far.cuda(), (32, 48), bg.cuda(),
+                                           mine_g.means, mine_g.covariances, mine_g.harmonics, mine_g.opacities)
+        assert mine.shape == (b, 3, 32, 48) and float(ref.abs().max()) > 0
+        (mine * w.cuda()).sum().backward()
+        assert ((mine.detach().cpu() - ref.detach()).abs() > 1e-5).float().mean() <= 2e-3
+        for got, want in ((mine_g.means, ref_g.means), (mine_g.covariances, ref_g.covariances), (mine_g.harmonics, ref_g.harmonics),
+                          (mine_g.opacities, ref_g.opacities)):
+            scale = float(want.grad.abs().max())
+            e = (got.grad.cpu() - want.grad).abs()
+            assert float(torch.quantile(e.flatten(), 0.999)) <= 1e-4 * scale and float(e.max()) <= 5e-2 * scale
 
 
 def test_huge_footprints_split_views_and_stay_correct():

@@ -143,3 +143,24 @@ def test_comparator_glue_restates_the_reference_glue(name, depth_mode):
     loss1.backward(); loss2.backward()
     for a, b in ((g1.means, g2.means), (g1.covariances, g2.covariances), (g1.harmonics, g2.harmonics), (g1.opacities, g2.opacities)):
         assert torch.equal(a.grad, b.grad)
+
+
+def test_comparator_glue_restates_the_reference_orthographic_variant():
+    """cuda_splatting.py:129-219 (one view, as the reference uses it): the restatement the GPU box checks the product
+    against equals the unmodified reference, images and gradients, both over the CPU oracle."""
+    from baseline import per_view_glue
+    from oracle import ext_compat
+    cs = load_reference_cuda_splatting(ext_compat)
+    scene = make_scene("tiny")
+    g1, g2 = leaf_gaussians(scene), leaf_gaussians(scene)
+    ext = scene.extrinsics[0, :1]
+    width, height, near, far = torch.tensor([3.0]), torch.tensor([2.0]), torch.tensor([0.0]), torch.tensor([20.0])
+    args = lambda g: (ext, width, height, near, far, (32, 48), torch.zeros(1, 3), g.means[:1], g.covariances[:1], g.harmonics[:1], g.opacities[:1])
+    a = cs.render_cuda_orthographic(*args(g1))
+    b = per_view_glue.render_cuda_orthographic(ext_compat, *args(g2))
+    assert float(a.abs().max()) > 0 and torch.equal(a, b)
+    gen = torch.Generator().manual_seed(4)
+    w = torch.randn(a.shape, generator=gen)
+    (a * w).sum().backward(); (b * w).sum().backward()
+    for x, y in ((g1.means, g2.means), (g1.covariances, g2.covariances), (g1.harmonics, g2.harmonics), (g1.opacities, g2.opacities)):
+        assert torch.equal(x.grad, y.grad)
