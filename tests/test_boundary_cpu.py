@@ -132,3 +132,33 @@ def test_gpu_comparator_library_loads():
     L = upstream_ext.load()
     for name in ("ups_preprocess", "ups_bin_render", "ups_backward", "ups_scan_temp_bytes", "ups_sort_temp_bytes"):
         assert hasattr(L, name)
+
+
+def test_plan_regions_are_disjoint_aligned_and_in_bounds():
+    """Every region of the two caller-owned workspaces, at its documented size (include/b200splat.h), lies inside the
+    workspace, starts 256-byte aligned and overlaps no other region -- for random problem sizes, including pair
+    capacities that are no multiple of the sort tile."""
+    import random
+    rnd = random.Random(7)
+    SORT_TILE = 3072
+    for _ in range(200):
+        B = rnd.choice([1, 1, 2, 8]); N = rnd.randint(1, 3_000_000); V = rnd.randint(1, 12); VV = B * V
+        H, W = rnd.randint(1, 2000), rnd.randint(1, 2000)
+        if (H + 15) // 16 > 255 or (W + 15) // 16 > 255:
+            continue
+        cap = rnd.randint(1, 1 << rnd.randint(4, 31))
+        p = _lib.plan(B, N, VV, H, W, cap)
+        tickets = p.pre_tickets
+        assert tickets == VV * ((N + 255) // 256)
+        sort_tiles = (cap + SORT_TILE - 1) // SORT_TILE + 1
+        saved = [(p.off_status, 64), (p.off_rec, VV * N * 64), (p.off_vals_a, cap * 4), (p.off_ranges, p.bins * 8),
+                 (p.off_final_T, VV * H * W * 4), (p.off_n_contrib, VV * H * W * 4)]
+        scratch = [(p.off_keys_a, cap * 8), (p.off_keys_b, cap * 8), (p.off_vals_b, cap * 4), (p.off_scan_state, tickets * 8),
+                   (p.off_ticket_totals, tickets * 4), (p.off_scan_blocks, (tickets // 2048 + 1) * 8), (p.off_bin_info, tickets * 256 * 8),
+                   (p.off_hist, 8 * 256 * 4), (p.off_lookback, 2 * sort_tiles * 256 * 8), (p.off_counters, 64 * 4)]
+        for regions, total in ((saved, p.saved_bytes), (scratch, p.scratch_bytes)):
+            regions = sorted(regions)
+            for (o, n), (o2, _) in zip(regions, regions[1:] + [(total, 0)]):
+                assert o % 256 == 0 and o + n <= o2, (B, N, VV, H, W, cap, o, n, o2)
+        # the backward's gradient records reuse the scratch from its start
+        assert p.off_grad_rec + VV * N * 48 <= p.scratch_bytes
