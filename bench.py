@@ -109,26 +109,35 @@ def oracle_step_inputs(scene, view: int):
     return per_view_extension_inputs(scene, 0, view)
 
 
-def time_oracle(scene, steps: int, warmup: int, threads: int):
-    """CPU arm: the oracle's forward + backward of ONE target view (all Gaussians, full resolution),
-    OpenMP over tiles / Gaussians on `threads` host threads.  Returns (Mpix/s, seconds per step)."""
-    os.environ["OMP_NUM_THREADS"] = str(threads)
+def time_oracle(scene, views, steps: int, warmup: int, budget_s: float = 0.0):
+    """CPU arm: per step, the oracle's forward + backward of every view in `views` (all Gaussians, full resolution),
+    OpenMP over tiles / Gaussians on every host core this process may use -- set through omp_set_num_threads, because
+    under torchrun the environment says OMP_NUM_THREADS=1.  With a time budget, the step count is cut (never below 1)
+    so that the run ends in time.  Returns (Mpix/s, seconds per step, steps actually timed, threads)."""
     from oracle import splat_oracle as so
+    threads = so.set_threads()
     so.set_parallel_backward(True)
-    inp = oracle_step_inputs(scene, 0)
-    g = scene.grad_color[0, 0].numpy()
+    inps = [oracle_step_inputs(scene, v) for v in views]
+    grads = [scene.grad_color[0, v].numpy() for v in views]
     H, W = scene.image_shape
     ts = []
-    for i in range(warmup + steps):
+    t_start = time.perf_counter()
+    i = 0
+    while i < warmup + steps:
         t0 = time.perf_counter()
-        st = so.forward_view(**inp)
-        so.backward_view(st, g)
-        st.close()
+        for inp, g in zip(inps, grads):
+            st = so.forward_view(**inp)
+            so.backward_view(st, g)
+            st.close()
+        dt = time.perf_counter() - t0
         if i >= warmup:
-            ts.append(time.perf_counter() - t0)
+            ts.append(dt)
+        i += 1
+        if budget_s and ts and (time.perf_counter() - t_start) + dt > budget_s:
+            break
     so.set_parallel_backward(False)
     sec = sum(ts) / len(ts)
-    return H * W / sec / 1e6, sec
+    return len(views) * H * W / sec / 1e6, sec, len(ts), threads
 
 
 def run_reference(args):
@@ -137,18 +146,19 @@ def run_reference(args):
         return
     from my_depthsplat_b200.scenes import CONFIGS, make_scene
     cfg = CONFIGS[args.config]
-    scene = make_scene(cfg, v_tgt=1)
-    threads = os.cpu_count() or 1
-    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    mpix, sec = time_oracle(scene, steps, warmup, threads)
+    V = args.views or cfg.v_tgt
+    scene = make_scene(cfg, v_tgt=V)   # the views one GPU of the repo arm renders per step
+    N = scene.gaussians.means.shape[1]
     H, W = scene.image_shape
-    sample = f"1 target view {H}x{W}, all {scene.gaussians.means.shape[1]} Gaussians, fwd+bwd, {steps} steps"
+    mpix, sec, steps, threads = time_oracle(scene, list(range(V)), args.steps, args.warmup, budget_s=float(os.environ.get("B200S_REF_BUDGET_S", "420")))
+    sample = f"{V} target views {H}x{W} per step, all {N} Gaussians, fwd+bwd, {steps} timed steps after {args.warmup} warm-up, {sec:.2f} s each"
     line = {
         "impl": "reference", "metric": "rasterizer fwd+bwd Mpix/s", "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload_name(cfg, scene, 4), "note": "reference arm = CPU oracle port (the reference's CUDA extension "
-                   "diff_gaussian_rasterization is not installable here and the reference has no CPU rasterizer)"},
+        "config": {"workload": _workload_name(cfg, scene, V), "views_per_gpu": V, "gaussians": N, "height": H, "width": W,
+                   "note": "reference arm = CPU oracle port on the host cores (the reference's CUDA extension diff_gaussian_rasterization "
+                           "is not installable here and the reference has no CPU rasterizer); one step = the V views one GPU renders"},
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -358,7 +368,8 @@ def run_ours(args):
         render_views(*((devt[k] if by_scene else shard_views(devt[k], world, rank)) for k in ("extrinsics", "intrinsics", "near", "far")), (H, W), decoder.background_color,
                      devt["means"], devt["covariances"], devt["harmonics"], devt["opacities"], count_work=True)
     st = R.last_stats
-    plan = _lib.plan(B_local, N, B_local * V, H, W, max(st.num_pairs, 1))
+    plan = _lib.plan(B_local, N, B_local * V, H, W, max(st.num_pairs, 1), R._SORT_MODES[R.sort_mode])
+    binned = plan.sort_mode == _lib.SORT_BINNED
 
     hbm_peak, sm_max, peak_src = _peaks()
     sm_mhz = clocks["sm_mhz"] or sm_max
@@ -366,7 +377,11 @@ def run_ours(args):
     Rn, Nv, P = st.num_pairs, st.num_visible, B_local * V * H * W
     NB = N * B_local  # Gaussians of all scenes of this rank's call
     alg = {  # algorithmic bytes / flops per launch
-        "pre_bin": ("hbm", 148.0 * NB * V + 64.0 * NB * V + 12.0 * Rn),
+        # projection (148 B read per Gaussian-view, L2-shared across views; 64 B record + 8 B binning word written), then
+        # GLOBAL: binning words read once, 12 B (key, value) per pair written; BINNED: binning words read twice (count,
+        # scatter), 8 B (depth bits, index) per pair written
+        "pre_bin": ("hbm", (148.0 + 64.0 + 8.0) * NB * V + ((16.0 * NB * V + 8.0 * Rn) if binned else (8.0 * NB * V + 12.0 * Rn))),
+        "bin_sort": ("hbm", 12.0 * Rn),   # every bin read once (8 B per pair), its sorted indices written once (4 B)
         "sort_hist": ("hbm", 8.0 * Rn),
         "sort_passes": ("hbm", 24.0 * Rn * plan.sort_passes),
         "ranges": ("hbm", 8.0 * Rn + 8.0 * plan.bins),
@@ -412,10 +427,9 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        mpix, sec = time_oracle(make_scene(cfg, v_tgt=1), 2, 1, threads)
+        mpix, sec, nrun, threads = time_oracle(make_scene(cfg, v_tgt=V), [0], 2, 1)
         cpu_baseline = {"value": round(mpix, 4), "unit": "Mpix/s", "cores": threads, "kind": "port",
-                        "sample": f"1 of the {V} target views ({H}x{W}, all {N} Gaussians), fwd+bwd, mean of 2 runs, {sec:.2f} s each"}
+                        "sample": f"1 of the {V} target views ({H}x{W}, all {N} Gaussians), fwd+bwd, mean of {nrun} runs, {sec:.2f} s each"}
 
     # ---- GPU comparator: the upstream DESIGN (per-view calls, V-fold replication, CUB sort, block-synchronous tiles,
     # per-pixel atomics) restated in baseline/ and driven by the reference's restated glue, same scene, same GPU ------
@@ -467,7 +481,7 @@ def run_ours(args):
             "stages": stage_report,
             "between_calls_ms": round(gap_ms, 4),
             "work": {"pairs": Rn, "visible": Nv, "tested": st.tested, "blended": st.blended, "max_tile_len": st.max_tile_len,
-                     "sort_passes": plan.sort_passes, "pixels_per_step": pix_step},
+                     "sort_mode": R.sort_mode, "sort_passes": 0 if binned else plan.sort_passes, "pixels_per_step": pix_step},
             "cpu_baseline": cpu_baseline,
             "gpu_baseline": gpu_baseline,
         }

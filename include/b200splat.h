@@ -20,7 +20,9 @@
  *   - the caller owns every buffer (inputs, outputs, the two workspaces); the library never
  *     allocates, frees or synchronises; all work is enqueued on the `stream` argument
  *     (a cudaStream_t passed as void*);
- *   - re-entrant, no global state;
+ *   - re-entrant: nothing a call computes depends on process state.  The only process-wide state is opt-in and
+ *     debug-only -- the stage profiler (b200s_profile_*), the launch counter and the A/B knobs of b200s_debug_set, which
+ *     select between kernel variants with identical results -- plus per-device caches of device attributes;
  *   - return value: B200S_OK, or B200S_EBADARG (nothing enqueued), or B200S_ECUDA (a launch failed;
  *     `b200s_last_cuda_error` holds the code).  Capacity overflow of the (tile,depth) pair buffers
  *     is NOT a return code: it is reported in the device status block (B200sStatus) so that the
@@ -36,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 6
+#define B200S_ABI_VERSION 7
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -79,9 +81,21 @@ typedef struct B200sViews {
   const float* depth_clamp;   /* [VV,2] (near, far) for B200S_DEPTH_LOG; may be NULL otherwise */
 } B200sViews;
 
+/* How the (tile, Gaussian) pairs get into per-(view, tile) depth order -- what cub::DeviceRadixSort::SortPairs +
+ * identifyTileRanges do behind _C.rasterize_gaussians.  Both modes produce the same lists and ranges, bit for bit.
+ *   BINNED (default): per-bin pair counts by warp-aggregated atomics -> one scan = the tile ranges -> (depth bits, index)
+ *     entries scattered into their bin (one atomic claim per run of lanes with the same bin) -> ONE CTA per bin orders
+ *     its segment by (depth bits, index) with LSD counting passes in shared memory over the significant bits of
+ *     (depth - bin minimum).  20 bytes of HBM traffic per pair.  Bins of more than 11 008 entries run the same passes on
+ *     global (L2-resident) ping-pong buffers: no limit on the bin length.
+ *   GLOBAL: one stable onesweep LSD radix sort of all 64-bit (view | tile | depth) keys, 8 bits per pass, then a
+ *     range-finding pass.  24 bytes per pair per pass. */
+enum { B200S_SORT_BINNED = 0, B200S_SORT_GLOBAL = 1 };
+
 /* Problem dimensions -> workspace plan. */
 typedef struct B200sDims {
   int32_t num_scenes, num_gaussians, num_views, height, width;
+  int32_t sort_mode;     /* B200S_SORT_* */
   int64_t pair_capacity; /* R_cap: capacity of the (key,value) pair buffers, < 2^32 - 8192 (list positions are 32-bit) */
 } B200sDims;
 
@@ -115,6 +129,13 @@ typedef struct B200sPlan {
   size_t off_lookback;           /* [2, sort_tiles_cap, 256] u64 onesweep look-back words */
   size_t off_counters;           /* [64] u32 ticket / tile counters */
   size_t off_grad_rec;           /* backward only: [VV,N] 48-byte gradient records (may alias keys) */
+  /* BINNED mode (off_keys_a then holds the [R_cap] 8-byte (depth bits, Gaussian index) entries, keys_b / vals_b the
+   * ping-pong and rank buffers of the bins too long for shared memory; lookback is empty) */
+  int32_t sort_mode;             /* B200S_SORT_* the plan was made for */
+  int32_t bin_sort_cap;          /* longest bin the segment sort keeps in shared memory */
+  size_t off_bin_count;          /* [bins] u32 pairs per (view, tile) bin */
+  size_t off_bin_cursor;         /* [bins] u32 next free position of every bin during the scatter */
+  size_t off_long_list;          /* [4, bins] u32 bin ids per size class of the segment sort */
 } B200sPlan;
 
 /* Device status block (first bytes of the saved workspace). */
@@ -125,7 +146,8 @@ typedef struct B200sStatus {
   uint64_t tested;        /* optional flop accounting (filled when B200sOut.count_work != 0) */
   uint64_t blended;
   uint32_t max_tile_len;  /* longest per-tile list */
-  uint32_t reserved[5];
+  uint32_t max_bin_len;   /* BINNED mode: longest bin, known right after the scan of the bin counts */
+  uint32_t reserved[4];
 } B200sStatus;
 
 typedef struct B200sOut {
@@ -134,8 +156,9 @@ typedef struct B200sOut {
   int32_t* radii;    /* [VV,N] or NULL */
   int32_t count_work;/* != 0: accumulate tested/blended/max_tile_len into the status block */
   void* status_host; /* optional: DEVICE-ACCESSIBLE pointer to 16 bytes of mapped pinned host memory (b200s_host_alloc).
-                        Stage A stores {u64 num_pairs, u32 overflow, u32 1} there directly from the kernel, so the
-                        host can read the pair count after an event wait without occupying a copy engine. */
+                        Stage A stores {u64 num_pairs, u32 overflow flag, u32 nonzero marker (BINNED: 0x80000000 |
+                        max_bin_len)} there directly from the kernel, so the host can read the pair count after an
+                        event wait (or lazily, much later) without occupying a copy engine. */
 } B200sOut;
 
 typedef struct B200sGradOut { /* upstream gradients */
@@ -193,11 +216,20 @@ size_t b200s_sort_tmp_bytes(int64_t n);
 int b200s_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, int32_t bits,
                      void* tmp, void* stream);
 
+/* Stand-alone BINNED-mode segment sort (the kernels forward uses, exported for the parity tests and micro-benchmarks):
+ * `entries` holds n 8-byte (key: low word, value: high word) pairs grouped by bin -- bin b owns the bin_counts[b] pairs
+ * after those of bins 0..b-1 -- in arbitrary order inside a bin.  Writes ranges_out[bins][2] = (start, end) of every bin
+ * and vals_out[n] = the values of every bin in ascending (key, value) order.  `entries` is clobbered.  `tmp` needs
+ * b200s_segment_sort_tmp_bytes(n, bins) bytes. */
+size_t b200s_segment_sort_tmp_bytes(int64_t n, int32_t bins);
+int b200s_segment_sort(const uint32_t* bin_counts, int32_t bins, uint64_t* entries, int64_t n, uint32_t* vals_out, uint32_t* ranges_out,
+                       void* tmp, void* stream);
+
 /* Optional per-stage device timing (CUDA events recorded on the caller's stream at stage boundaries;
  * off by default, process-wide).  bench.py uses it for the per-kernel roofline numbers. */
 enum { B200S_STAGE_PRE_BIN = 0, B200S_STAGE_SORT_HIST = 1, B200S_STAGE_SORT_PASSES = 2, B200S_STAGE_RANGES = 3,
        B200S_STAGE_COMP_FWD = 4, B200S_STAGE_GRAD_ZERO = 5, B200S_STAGE_COMP_BWD = 6, B200S_STAGE_PRE_BWD = 7,
-       B200S_STAGE_END = 8, B200S_NUM_STAGES = 9 };
+       B200S_STAGE_END = 8, B200S_STAGE_BIN_SORT = 9 /* BINNED mode: the per-bin segment sort */, B200S_NUM_STAGES = 10 };
 void b200s_profile_enable(int on);
 /* Synchronises on the recorded events, ADDS the elapsed milliseconds of every stage recorded since the
  * last read into ms_by_stage[B200S_NUM_STAGES], clears the recording.  Returns the number of stages seen. */

@@ -10,12 +10,13 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200splat.so"
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 B200S_OK, B200S_EBADARG, B200S_ECUDA = 0, 1, 3
 COV_3X3, COV_UPPER6 = 0, 1
 SH_CHANNEL_MAJOR, SH_COEFF_MAJOR = 0, 1
 DEPTH_NONE, DEPTH_Z, DEPTH_DISPARITY, DEPTH_LOG = 0, 1, 2, 3
+SORT_BINNED, SORT_GLOBAL = 0, 1
 
 _f32p = C.c_void_p  # device pointers travel as integers
 
@@ -39,7 +40,7 @@ class Views(C.Structure):
 class Dims(C.Structure):
     _fields_ = [
         ("num_scenes", C.c_int32), ("num_gaussians", C.c_int32), ("num_views", C.c_int32), ("height", C.c_int32),
-        ("width", C.c_int32), ("pair_capacity", C.c_int64),
+        ("width", C.c_int32), ("sort_mode", C.c_int32), ("pair_capacity", C.c_int64),
     ]
 
 
@@ -54,13 +55,15 @@ class Plan(C.Structure):
         ("off_scan_state", C.c_size_t), ("off_ticket_totals", C.c_size_t), ("off_scan_blocks", C.c_size_t),
         ("off_bin_info", C.c_size_t), ("off_hist", C.c_size_t), ("off_lookback", C.c_size_t), ("off_counters", C.c_size_t),
         ("off_grad_rec", C.c_size_t),
+        ("sort_mode", C.c_int32), ("bin_sort_cap", C.c_int32), ("off_bin_count", C.c_size_t), ("off_bin_cursor", C.c_size_t),
+        ("off_long_list", C.c_size_t),
     ]
 
 
 class Status(C.Structure):
     _fields_ = [
         ("num_pairs", C.c_uint64), ("overflow", C.c_uint32), ("num_visible", C.c_uint32), ("tested", C.c_uint64),
-        ("blended", C.c_uint64), ("max_tile_len", C.c_uint32), ("reserved", C.c_uint32 * 5),
+        ("blended", C.c_uint64), ("max_tile_len", C.c_uint32), ("max_bin_len", C.c_uint32), ("reserved", C.c_uint32 * 4),
     ]
 
 
@@ -85,9 +88,9 @@ EXPORTS = (
     "b200s_plan", "b200s_forward_bin", "b200s_forward_render", "b200s_backward", "b200s_sort_tmp_bytes",
     "b200s_sort_pairs", "b200s_abi_version", "b200s_last_cuda_error", "b200s_build_info", "b200s_profile_enable",
     "b200s_profile_read", "b200s_kernel_launches", "b200s_debug_set", "b200s_host_alloc", "b200s_host_free",
-    "b200s_nvls_allreduce",
+    "b200s_nvls_allreduce", "b200s_segment_sort", "b200s_segment_sort_tmp_bytes",
 )
-STAGES = ("pre_bin", "sort_hist", "sort_passes", "ranges", "comp_fwd", "grad_zero", "comp_bwd", "pre_bwd", "end")
+STAGES = ("pre_bin", "sort_hist", "sort_passes", "ranges", "comp_fwd", "grad_zero", "comp_bwd", "pre_bwd", "end", "bin_sort")
 
 _lib = None
 
@@ -137,6 +140,10 @@ def load() -> C.CDLL:
     L.b200s_host_free.argtypes = [C.c_void_p]
     L.b200s_nvls_allreduce.restype = C.c_int
     L.b200s_nvls_allreduce.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int, C.c_void_p]
+    L.b200s_segment_sort_tmp_bytes.restype = C.c_size_t
+    L.b200s_segment_sort_tmp_bytes.argtypes = [C.c_int64, C.c_int32]
+    L.b200s_segment_sort.restype = C.c_int
+    L.b200s_segment_sort.argtypes = [vp, C.c_int32, vp, C.c_int64, vp, vp, vp, vp]
     L.b200s_debug_set.restype = None
     L.b200s_debug_set.argtypes = [C.c_int, C.c_int]
     if L.b200s_abi_version() != ABI_VERSION:
@@ -155,8 +162,9 @@ def check(rc: int, what: str) -> None:
     raise RuntimeError(f"{what}: unknown return code {rc}")
 
 
-def plan(num_scenes: int, num_gaussians: int, num_views: int, height: int, width: int, pair_capacity: int) -> Plan:
-    d = Dims(num_scenes, num_gaussians, num_views, height, width, pair_capacity)
+def plan(num_scenes: int, num_gaussians: int, num_views: int, height: int, width: int, pair_capacity: int,
+         sort_mode: int = SORT_BINNED) -> Plan:
+    d = Dims(num_scenes, num_gaussians, num_views, height, width, sort_mode, pair_capacity)
     p = Plan()
     check(load().b200s_plan(C.byref(d), C.byref(p)), "b200s_plan")
     return p

@@ -39,14 +39,30 @@ static int fail(cudaError_t e) {
   g_last_cuda_error = (int)e;
   return B200S_ECUDA;
 }
-static int sm_count() {
-  static thread_local int n = 0;
+// SM count of the CURRENT device (cached per device id: one process may drive several GPUs, from one thread or many)
+namespace b200s {
+int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const int slot = dev & 63;
+  int n = cache[slot].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[slot].store(n, std::memory_order_relaxed);
   }
   return n;
 }
+bool first_use_on_device(std::atomic<unsigned long long>& seen) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (seen.load(std::memory_order_relaxed) & bit) return false;
+  seen.fetch_or(bit, std::memory_order_relaxed);
+  return true;
+}
+}  // namespace b200s
+static int sm_count() { return b200s::device_sm_count(); }
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 static int bits_for(int n) { int b = 0; while ((1 << b) < n) b++; return b; }
 
@@ -76,7 +92,7 @@ void* b200s_host_alloc(size_t bytes) {
   return p;
 }
 void b200s_host_free(void* p) { if (p) cudaFreeHost(p); }
-void b200s_debug_set(int which, int value) { if (which >= 0 && which < 4) b200s::g_sort_knobs[which] = value; }
+void b200s_debug_set(int which, int value) { if (which >= 0 && which < 4) b200s::g_sort_knobs[which].store(value, std::memory_order_relaxed); }
 long long b200s_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 int b200s_last_cuda_error(void) { return g_last_cuda_error; }
 const char* b200s_build_info(void) {
@@ -108,6 +124,10 @@ int b200s_plan(const B200sDims* d, B200sPlan* p) {
   p->sort_bits = 32 + p->tile_bits + p->view_bits;
   p->sort_passes = (p->sort_bits + 7) / 8;
   if (p->sort_passes > 8) return B200S_EBADARG;
+  if (d->sort_mode != B200S_SORT_BINNED && d->sort_mode != B200S_SORT_GLOBAL) return B200S_EBADARG;
+  p->sort_mode = d->sort_mode;
+  p->bin_sort_cap = BIN_CAP_L;
+  const bool binned = d->sort_mode == B200S_SORT_BINNED;
   // list positions (tile ranges, sort scatter) are 32-bit
   if (d->pair_capacity >= (1ll << 32) - 8192) return B200S_EBADARG;
   const long long chunks = (d->num_gaussians + PRE_THREADS - 1) / PRE_THREADS;
@@ -128,6 +148,8 @@ int b200s_plan(const B200sDims* d, B200sPlan* p) {
   p->off_n_contrib = o; o = align_up(o + VP * 4);
   p->saved_bytes = o;
   o = 0;
+  // GLOBAL: key ping-pong + value pong.  BINNED: keys_a = the (depth bits, index) entries, keys_b / vals_b = the ping-pong and
+  // rank buffers of bins too long for shared memory (same sizes, so the two modes need the same scratch)
   p->off_keys_a = o; o = align_up(o + R * 8);
   p->off_keys_b = o; o = align_up(o + R * 8);
   p->off_vals_b = o; o = align_up(o + R * 4);
@@ -136,8 +158,11 @@ int b200s_plan(const B200sDims* d, B200sPlan* p) {
   p->off_scan_blocks = o; o = align_up(o + ((size_t)p->pre_tickets / 2048 + 2) * 8);
   p->off_bin_info = o; o = align_up(o + (size_t)p->pre_tickets * PRE_THREADS * 8);
   p->off_hist = o; o = align_up(o + 8 * 256 * 4);
-  p->off_lookback = o; o = align_up(o + 2 * (size_t)p->sort_tiles_cap * 256 * 8);
+  p->off_lookback = o; o = align_up(o + (binned ? 0 : 2 * (size_t)p->sort_tiles_cap * 256 * 8));
   p->off_counters = o; o = align_up(o + CNT_WORDS * 4);
+  p->off_bin_count = o; o = align_up(o + (binned ? (size_t)p->bins * 4 : 0));
+  p->off_bin_cursor = o; o = align_up(o + (binned ? (size_t)p->bins * 4 : 0));
+  p->off_long_list = o; o = align_up(o + (binned ? (size_t)BIN_CLASSES * p->bins * 4 : 0));
   const size_t fwd_bytes = o;
   p->off_grad_rec = 0;  // backward reuses the scratch from its start (keys are dead by then)
   const size_t bwd_bytes = align_up(VN * GREC_FLOATS * 4);
@@ -186,13 +211,22 @@ int b200s_forward_render(const B200sScene* sc, const B200sViews* vw, const B200s
   uint64_t* keys_b = reinterpret_cast<uint64_t*>(scratch + pl->off_keys_b);
   uint32_t* vals_a = reinterpret_cast<uint32_t*>(saved + pl->off_vals_a);
   uint32_t* vals_b = reinterpret_cast<uint32_t*>(scratch + pl->off_vals_b);
-  cudaError_t e = launch_sort(keys_a, vals_a, keys_b, vals_b, pl->sort_passes, pl->pair_capacity, cnt, reinterpret_cast<uint32_t*>(scratch + pl->off_hist),
-                              reinterpret_cast<uint64_t*>(scratch + pl->off_lookback), reinterpret_cast<uint32_t*>(scratch + pl->off_counters), sm_count(), stream,
-                              /*hist_ready=*/true);
-  if (e != cudaSuccess) return fail(e);
   uint2* ranges = reinterpret_cast<uint2*>(saved + pl->off_ranges);
-  e = launch_tile_ranges(keys_a, cnt, ranges, pl->bins, pl->pair_capacity, sm_count(), stream);
-  if (e != cudaSuccess) return fail(e);
+  cudaError_t e;
+  if (pl->sort_mode == B200S_SORT_BINNED) {
+    uint32_t* counters = reinterpret_cast<uint32_t*>(scratch + pl->off_counters);
+    BinSortWork w{reinterpret_cast<uint32_t*>(scratch + pl->off_long_list), counters + CNT_BIN_CLASS_COUNT, counters + CNT_BIN_CLASS_NEXT};
+    e = launch_bin_sort(reinterpret_cast<uint2*>(keys_a), reinterpret_cast<uint2*>(keys_b), vals_b, ranges, vals_a, w, pl->bins, &st->overflow,
+                        sm_count(), stream);
+    if (e != cudaSuccess) return fail(e);
+  } else {
+    e = launch_sort(keys_a, vals_a, keys_b, vals_b, pl->sort_passes, pl->pair_capacity, cnt, reinterpret_cast<uint32_t*>(scratch + pl->off_hist),
+                    reinterpret_cast<uint64_t*>(scratch + pl->off_lookback), reinterpret_cast<uint32_t*>(scratch + pl->off_counters), sm_count(), stream,
+                    /*hist_ready=*/true);
+    if (e != cudaSuccess) return fail(e);
+    e = launch_tile_ranges(keys_a, cnt, ranges, pl->bins, pl->pair_capacity, sm_count(), stream);
+    if (e != cudaSuccess) return fail(e);
+  }
   CompArgs a;
   memset(&a, 0, sizeof(a));
   a.N = sc->num_gaussians; a.H = vw->height; a.W = vw->width; a.grid_x = pl->grid_x; a.tile_bits = pl->tile_bits;
@@ -241,6 +275,31 @@ int b200s_backward(const B200sScene* sc, const B200sViews* vw, const B200sPlan* 
   if (!(stages & 2)) { stage_mark(B200S_STAGE_END, stream); return B200S_OK; }
   e = launch_preprocess_bwd(*sc, *vw, *pl, saved, scratch, *gin, stream);
   stage_mark(B200S_STAGE_END, stream);
+  return e == cudaSuccess ? B200S_OK : fail(e);
+}
+
+size_t b200s_segment_sort_tmp_bytes(int64_t n, int32_t bins) {
+  if (n < 0 || bins <= 0) return 0;
+  return align_up((size_t)n * 8) + align_up((size_t)n * 4) + align_up((size_t)bins * 4) + align_up((size_t)BIN_CLASSES * bins * 4) +
+         align_up(sizeof(B200sStatus)) + align_up(CNT_WORDS * 4);
+}
+
+int b200s_segment_sort(const uint32_t* bin_counts, int32_t bins, uint64_t* entries, int64_t n, uint32_t* vals_out, uint32_t* ranges_out, void* tmp,
+                       void* stream_) {
+  if (!bin_counts || bins <= 0 || !entries || n < 0 || !vals_out || !ranges_out || !tmp || n >= (1ll << 32) - 8192) return B200S_EBADARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* t = (char*)tmp;
+  uint2* entries_tmp = reinterpret_cast<uint2*>(t); t += align_up((size_t)n * 8);
+  uint32_t* rank_tmp = reinterpret_cast<uint32_t*>(t); t += align_up((size_t)n * 4);
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(t); t += align_up((size_t)bins * 4);
+  uint32_t* lists = reinterpret_cast<uint32_t*>(t); t += align_up((size_t)BIN_CLASSES * bins * 4);
+  B200sStatus* st = reinterpret_cast<B200sStatus*>(t); t += align_up(sizeof(B200sStatus));
+  uint32_t* counters = reinterpret_cast<uint32_t*>(t);
+  BinSortWork w{lists, counters + CNT_BIN_CLASS_COUNT, counters + CNT_BIN_CLASS_NEXT};
+  cudaError_t e = launch_bin_scan(bin_counts, bins, reinterpret_cast<uint2*>(ranges_out), cursor, w, st, (unsigned long long)n, nullptr, stream);
+  if (e != cudaSuccess) return fail(e);
+  e = launch_bin_sort(reinterpret_cast<uint2*>(entries), entries_tmp, rank_tmp, reinterpret_cast<const uint2*>(ranges_out), vals_out, w, bins,
+                      &st->overflow, sm_count(), stream);
   return e == cudaSuccess ? B200S_OK : fail(e);
 }
 

@@ -1,0 +1,257 @@
+// binsort.cu -- BINNED sort mode: every (view, tile) bin's entries are put into depth order by ONE CTA, in shared
+// memory.  Together with the counting / scattering kernels of preprocess.cu this replaces
+// cub::DeviceRadixSort::SortPairs + identifyTileRanges behind _C.rasterize_gaussians: instead of
+// six global passes over 64-bit (view | tile | depth) keys (24 B of HBM traffic per pair per pass), the pairs are
+// scattered straight into their bin (8 B written), and each bin is read once (8 B) and its sorted Gaussian indices
+// written once (4 B).
+//
+// Order inside a bin = the order the stable global sort produces: ascending depth bits, ties in ascending Gaussian
+// index (the global sort is stable and pairs are emitted in index order).  The scatter claims positions with atomics,
+// so the arrival order is arbitrary; the segment sort therefore orders by the pair (depth bits, index):
+//   1. load the bin, min / max of the depth bits -> b = significant bits of (depth - min);
+//   2. ceil(b / 8) stable LSD counting passes over 8-bit digits of (depth - min): each warp ranks a contiguous chunk
+//      (MATCH.ANY groups + one shared atomic per group give the stable rank inside the chunk), one block-wide scan of
+//      the [digit][warp] counters turns them into destinations, second sweep moves (key, index);
+//   3. equal-depth runs (rare: two Gaussians of a tile with the same float depth) are ordered by index: each member
+//      counts the smaller indices of its run.  A bin with a run longer than RUN_CAP is instead re-sorted with LSD
+//      passes over the index bits first (degenerate scenes: thousands of Gaussians at exactly the same depth);
+//   4. write the indices.
+// Four size classes, one launch each (the class lists are built on the device by bin_scan_kernel, CTAs fetch bins
+// from them dynamically): XS / S / L keep (key, index) ping-pong buffers + 16-bit ranks in shared memory at 4 / 2 / 1
+// CTAs per SM; XL (longer than CAP_L) runs the same passes on ping-pong buffers in global memory (L2-resident for the
+// sizes that occur), so there is no limit on the bin length.
+#include "kernels.cuh"
+
+namespace b200s {
+
+constexpr int BS_DIGITS = 256;
+constexpr int RUN_CAP = 32;
+
+struct BinSortArgs {
+  uint2* entries;            // [R] (depth bits, Gaussian index), grouped by bin, arbitrary order inside a bin
+  uint2* entries_tmp;        // [R] XL ping-pong
+  uint32_t* rank_tmp;        // [R] XL ranks
+  const uint2* ranges;       // [bins] (start, end)
+  uint32_t* vals_out;        // [R] sorted Gaussian indices
+  const uint32_t* list;      // bin ids of this size class
+  const uint32_t* count;     // how many
+  uint32_t* next;            // dynamic fetch counter
+  const uint32_t* overflow;
+};
+
+// ---- storage policies: where the (key, index) ping-pong and the ranks live -------------------------------------
+struct SmemStore {
+  uint32_t *kA, *vA, *kB, *vB;
+  uint16_t* rk;
+  __device__ __forceinline__ uint32_t key(uint32_t i) const { return kA[i]; }
+  __device__ __forceinline__ uint32_t val(uint32_t i) const { return vA[i]; }
+  __device__ __forceinline__ uint2 get(uint32_t i) const { return make_uint2(kA[i], vA[i]); }
+  __device__ __forceinline__ void put(uint32_t i, uint2 e) { kB[i] = e.x; vB[i] = e.y; }
+  __device__ __forceinline__ void set_rank(uint32_t i, uint32_t r) { rk[i] = (uint16_t)r; }
+  __device__ __forceinline__ uint32_t rank(uint32_t i) const { return rk[i]; }
+  __device__ __forceinline__ void swap() { uint32_t* t = kA; kA = kB; kB = t; t = vA; vA = vB; vB = t; }
+};
+struct GmemStore {
+  uint2 *A, *B;
+  uint32_t* rk;
+  __device__ __forceinline__ uint32_t key(uint32_t i) const { return A[i].x; }
+  __device__ __forceinline__ uint32_t val(uint32_t i) const { return A[i].y; }
+  __device__ __forceinline__ uint2 get(uint32_t i) const { return A[i]; }
+  __device__ __forceinline__ void put(uint32_t i, uint2 e) { B[i] = e; }
+  __device__ __forceinline__ void set_rank(uint32_t i, uint32_t r) { rk[i] = r; }
+  __device__ __forceinline__ uint32_t rank(uint32_t i) const { return rk[i]; }
+  __device__ __forceinline__ void swap() { uint2* t = A; A = B; B = t; }
+};
+
+// Block-wide exclusive scan of the [digit][warp] counters (digit-major, rows padded to W + 1 words so that a warp's
+// atomics on 32 different digits fall into 32 different banks): afterwards hist[d][w] = number of elements with a smaller
+// digit, or the same digit in an earlier warp chunk = the destination of warp w's first element with digit d.
+template <int T>
+__device__ __forceinline__ void scan_counters(uint32_t* hist, uint32_t* s_wtot) {
+  constexpr int W = T / 32, STR = W + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* p = hist + ((8 * tid) / W) * STR + (8 * tid) % W;  // eight consecutive warps of one digit
+  uint32_t c[8], s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { c[j] = p[j]; s += c[j]; }
+  uint32_t incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t t = lane < W ? s_wtot[lane] : 0u;
+    uint32_t x = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    s_wtot[lane] = x - t;
+  }
+  __syncthreads();
+  uint32_t run = s_wtot[warp] + incl - s;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { p[j] = run; run += c[j]; }
+}
+
+// One stable counting pass over the 8-bit digit `shift` of (key - sub) [ON_VAL: of (index - sub)].
+template <int T, bool ON_VAL, class Store>
+__device__ __forceinline__ void radix_pass(Store& st, uint32_t n, uint32_t sub, int shift, uint32_t* hist, uint32_t* s_wtot) {
+  constexpr int W = T / 32, STR = W + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int i = tid; i < BS_DIGITS * STR; i += T) hist[i] = 0;
+  __syncthreads();
+  const uint32_t chunk = ((n + W - 1) / W + 31u) & ~31u;
+  const uint32_t lo = min(n, warp * chunk), hi = min(n, lo + chunk);
+  uint32_t* col = hist + warp;
+  for (uint32_t base = lo; base < hi; base += 32) {
+    const uint32_t i = base + lane;
+    const bool valid = i < hi;
+    const uint32_t x = valid ? (ON_VAL ? st.val(i) : st.key(i)) : 0u;
+    const uint32_t d = valid ? ((x - sub) >> shift) & 255u : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t r = 0;
+    if (valid && lane == leader) r = atomicAdd(col + d * STR, (uint32_t)__popc(peers));
+    r = __shfl_sync(0xffffffffu, r, leader);
+    if (valid) st.set_rank(i, r + __popc(peers & lt));
+  }
+  __syncthreads();
+  scan_counters<T>(hist, s_wtot);
+  __syncthreads();
+  for (uint32_t base = lo; base < hi; base += 32) {
+    const uint32_t i = base + lane;
+    if (i < hi) {
+      const uint2 e = st.get(i);
+      const uint32_t d = (((ON_VAL ? e.y : e.x) - sub) >> shift) & 255u;
+      st.put(col[d * STR] + st.rank(i), e);
+    }
+  }
+  __syncthreads();
+  st.swap();
+}
+
+template <int T, class Store>
+__device__ __forceinline__ void sort_segment(Store& st, uint32_t n, uint32_t kmin, uint32_t kmax, uint32_t vmin, uint32_t vmax,
+                                             uint32_t* hist, uint32_t* s_wtot, uint32_t* s_flag, uint32_t* __restrict__ out) {
+  const int tid = threadIdx.x;
+  const int kbits = 32 - __clz(kmax - kmin);  // __clz(0) = 32
+  for (int shift = 0; shift < kbits; shift += 8) radix_pass<T, false>(st, n, kmin, shift, hist, s_wtot);
+  // a run of RUN_CAP + 1 equal depths?
+  if (tid == 0) *s_flag = 0;
+  __syncthreads();
+  {
+    bool lng = false;
+    for (uint32_t i = tid; i + RUN_CAP < n; i += T) lng |= st.key(i) == st.key(i + RUN_CAP);
+    if (lng) *s_flag = 1;
+  }
+  __syncthreads();
+  const bool long_run = *s_flag != 0;
+  if (long_run) {  // degenerate bin: order by (depth, index) with index passes first (LSD), then the depth passes again
+    const int vbits = 32 - __clz(vmax - vmin);
+    for (int shift = 0; shift < vbits; shift += 8) radix_pass<T, true>(st, n, vmin, shift, hist, s_wtot);
+    for (int shift = 0; shift < kbits; shift += 8) radix_pass<T, false>(st, n, kmin, shift, hist, s_wtot);
+  }
+  for (uint32_t i = tid; i < n; i += T) {
+    const uint2 e = st.get(i);
+    uint32_t pos = i;
+    if (!long_run) {
+      const bool eq_prev = i > 0 && st.key(i - 1) == e.x, eq_next = i + 1 < n && st.key(i + 1) == e.x;
+      if (eq_prev || eq_next) {  // member of an equal-depth run: its place is the number of smaller indices in the run
+        uint32_t s = i, t = i + 1, smaller = 0;
+        while (s > 0 && st.key(s - 1) == e.x) { s--; smaller += st.val(s) < e.y; }
+        while (t < n && st.key(t) == e.x) { smaller += st.val(t) < e.y; t++; }
+        pos = s + smaller;
+      }
+    }
+    out[pos] = e.y;
+  }
+}
+
+__device__ __forceinline__ void block_minmax(uint32_t kmn, uint32_t kmx, uint32_t vmn, uint32_t vmx, uint32_t* s_mm) {
+  kmn = __reduce_min_sync(0xffffffffu, kmn); kmx = __reduce_max_sync(0xffffffffu, kmx);
+  vmn = __reduce_min_sync(0xffffffffu, vmn); vmx = __reduce_max_sync(0xffffffffu, vmx);
+  if ((threadIdx.x & 31) == 0) { atomicMin(&s_mm[0], kmn); atomicMax(&s_mm[1], kmx); atomicMin(&s_mm[2], vmn); atomicMax(&s_mm[3], vmx); }
+}
+
+// XL = false: bins of at most CAP entries, ping-pong in shared memory; XL = true: any length, ping-pong in global memory
+template <int T, int CAP, int MIN_CTAS, bool XL>
+__global__ void __launch_bounds__(T, MIN_CTAS) bin_sort_kernel(const BinSortArgs a) {
+  constexpr int W = T / 32, STR = W + 1;
+  extern __shared__ __align__(16) uint32_t bs_smem[];
+  __shared__ uint32_t s_wtot[32];
+  __shared__ uint32_t s_mm[4];
+  __shared__ uint32_t s_flag, s_fetch;
+  if (*a.overflow) return;
+  uint32_t* hist = bs_smem;  // [256][W + 1]
+  const int tid = threadIdx.x;
+  const uint32_t nbins = *a.count;
+  for (;;) {
+    __syncthreads();  // the previous bin's readers of the shared state are done
+    if (tid == 0) { s_fetch = atomicAdd(a.next, 1u); s_mm[0] = 0xffffffffu; s_mm[1] = 0u; s_mm[2] = 0xffffffffu; s_mm[3] = 0u; }
+    __syncthreads();
+    if (s_fetch >= nbins) return;
+    const uint2 range = a.ranges[a.list[s_fetch]];
+    const uint32_t n = range.y - range.x;
+    uint32_t kmn = 0xffffffffu, kmx = 0u, vmn = 0xffffffffu, vmx = 0u;
+    if (XL) {
+      GmemStore st{a.entries + range.x, a.entries_tmp + range.x, a.rank_tmp + range.x};
+      for (uint32_t i = tid; i < n; i += T) {
+        const uint2 e = st.A[i];
+        kmn = min(kmn, e.x); kmx = max(kmx, e.x); vmn = min(vmn, e.y); vmx = max(vmx, e.y);
+      }
+      block_minmax(kmn, kmx, vmn, vmx, s_mm);
+      __syncthreads();
+      sort_segment<T>(st, n, s_mm[0], s_mm[1], s_mm[2], s_mm[3], hist, s_wtot, &s_flag, a.vals_out + range.x);
+    } else {
+      SmemStore st;
+      st.kA = hist + BS_DIGITS * STR; st.vA = st.kA + CAP; st.kB = st.vA + CAP; st.vB = st.kB + CAP;
+      st.rk = reinterpret_cast<uint16_t*>(st.vB + CAP);
+      const uint2* __restrict__ src = a.entries + range.x;
+      for (uint32_t i = tid; i < n; i += T) {
+        const uint2 e = src[i];
+        st.kA[i] = e.x; st.vA[i] = e.y;
+        kmn = min(kmn, e.x); kmx = max(kmx, e.x); vmn = min(vmn, e.y); vmx = max(vmx, e.y);
+      }
+      block_minmax(kmn, kmx, vmn, vmx, s_mm);
+      __syncthreads();
+      sort_segment<T>(st, n, s_mm[0], s_mm[1], s_mm[2], s_mm[3], hist, s_wtot, &s_flag, a.vals_out + range.x);
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+template <int T, int CAP, int MIN_CTAS, bool XL>
+static cudaError_t launch_class(BinSortArgs a, int cls, const BinSortWork& w, int bins, int sm_count, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)BS_DIGITS * (T / 32 + 1) * 4 + (XL ? 0 : (size_t)CAP * 18);
+  static std::atomic<unsigned long long> configured{0};  // bit per device: the attribute is per (function, device)
+  cudaError_t e;
+  if (first_use_on_device(configured)) {
+    if ((e = cudaFuncSetAttribute(bin_sort_kernel<T, CAP, MIN_CTAS, XL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(bin_sort_kernel<T, CAP, MIN_CTAS, XL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
+  }
+  a.list = w.class_list + (size_t)cls * bins;
+  a.count = w.class_count + cls;
+  a.next = w.class_next + cls;
+  const int grid = bins < sm_count * MIN_CTAS ? bins : sm_count * MIN_CTAS;
+  bin_sort_kernel<T, CAP, MIN_CTAS, XL><<<grid, T, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bin_sort(uint2* entries, uint2* entries_tmp, uint32_t* rank_tmp, const uint2* ranges, uint32_t* vals_out,
+                            const BinSortWork& w, int bins, const uint32_t* overflow, int sm_count, cudaStream_t stream) {
+  if (bins <= 0) return cudaSuccess;
+  BinSortArgs a;
+  a.entries = entries; a.entries_tmp = entries_tmp; a.rank_tmp = rank_tmp; a.ranges = ranges; a.vals_out = vals_out;
+  a.list = nullptr; a.count = nullptr; a.next = nullptr; a.overflow = overflow;
+  stage_mark(B200S_STAGE_BIN_SORT, stream);
+  cudaError_t e;
+  // longest first: the long bins of a skewed scene start while every SM is still free
+  if ((e = launch_class<1024, 0, 1, true>(a, 3, w, bins, sm_count, stream)) != cudaSuccess) return e;
+  if ((e = launch_class<1024, BIN_CAP_L, 1, false>(a, 2, w, bins, sm_count, stream)) != cudaSuccess) return e;
+  if ((e = launch_class<512, BIN_CAP_S, 2, false>(a, 1, w, bins, sm_count, stream)) != cudaSuccess) return e;
+  if ((e = launch_class<256, BIN_CAP_XS, 4, false>(a, 0, w, bins, sm_count, stream)) != cudaSuccess) return e;
+  count_launches(4);
+  return cudaSuccess;
+}
+
+}  // namespace b200s

@@ -220,6 +220,8 @@ __device__ __forceinline__ bool tma_ok(const void* src, int bytes) { return ((((
 // counters block layout (u32 indices)
 constexpr int CNT_PRE_TICKET = 0;
 constexpr int CNT_SORT_TILE0 = 8;  // + pass (8 passes)
+constexpr int CNT_BIN_CLASS_COUNT = 16;  // + class (4): bins per size class of the BINNED mode
+constexpr int CNT_BIN_CLASS_NEXT = 20;   // + class (4): their fetch counters
 constexpr int CNT_WORDS = 64;
 
 }  // namespace b200s

@@ -200,8 +200,13 @@ __device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, PixStat
   const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
   // ex2.approx (2 instructions, <= 2e-6 relative for the powers that can be live) instead of expf's 8: the backward
   // is held to 1e-4 of the gradient scale, not to the forward's 1e-5 on the image
-  const float G = __expf(power);
-  const float alpha = fminf(ALPHA_MAX, __fmul_rn(h1.w, G));
+  float G = __expf(power);
+  float araw = __fmul_rn(h1.w, G);
+  // the alpha >= 1/255 cut must fall exactly where the forward put it (same expf, same rounding): the approximate
+  // exponential is off by up to ~1e-6 relative, so within 1e-5 of the threshold the decision is retaken with expf
+  // (a handful of (pixel, entry) pairs per image take this branch)
+  if (fabsf(__fmaf_rn(araw, 255.0f, -1.0f)) < 1e-5f) { G = expf(power); araw = __fmul_rn(h1.w, G); }
+  const float alpha = fminf(ALPHA_MAX, araw);
   const bool live = h->pos < s.last_contributor && power <= 0.0f && alpha >= ALPHA_MIN;
   if (!__any_sync(0xffffffffu, live)) return false;
   const float4 h2 = h->q2;
@@ -358,7 +363,7 @@ cudaError_t launch_composite_bwd(const CompArgs& a, int tiles, int views, bool d
   // CTA per tile at three per SM (76 registers, 24 warps); four two-warp CTAs per tile measure the same as two four-warp
   // ones; capping the eight-warp kernel at 64 registers for four per SM spills and is slower (2.71 ms).
   // b200s_debug_set(2, 2) selects the eight-warp shape for A/B runs.
-  if (g_sort_knobs[2] == 2) {
+  if (g_sort_knobs[2].load(std::memory_order_relaxed) == 2) {
     if (depth) composite_bwd_kernel<true, 8, 3><<<grid, TILE_PIX, 0, stream>>>(a);
     else composite_bwd_kernel<false, 8, 3><<<grid, TILE_PIX, 0, stream>>>(a);
   } else {

@@ -1,5 +1,7 @@
 // kernels.cuh -- argument blocks and host launchers shared between api.cu and the kernel files.
 #pragma once
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200s {
@@ -34,7 +36,9 @@ struct CompArgs {
 void stage_mark(int stage, cudaStream_t stream);
 void count_launches(int n);
 cudaError_t launch_nvls_allreduce(float* multicast, unsigned long long n_floats, int rank, int world, int sm_count, cudaStream_t stream);
-extern int g_sort_knobs[4];
+extern std::atomic<int> g_sort_knobs[4];  // A/B switches of b200s_debug_set (debug only; never change results)
+int device_sm_count();                                       // of the current device, cached per device id
+bool first_use_on_device(std::atomic<unsigned long long>& seen);  // true once per (call site's mask, current device)
 
 cudaError_t launch_preprocess_bin(const B200sScene&, const B200sViews&, const B200sPlan&, char* saved, char* scratch, const B200sOut*,
                                   cudaStream_t);
@@ -43,6 +47,19 @@ int sort_tiles_for(long long n_cap);
 cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int passes, long long n_cap, CountRef cnt,
                         uint32_t* hist, uint64_t* lookback, uint32_t* counters, int sm_count, cudaStream_t, bool hist_ready);
 cudaError_t launch_tile_ranges(const uint64_t* keys, CountRef cnt, uint2* ranges, int bins, long long n_cap, int sm_count, cudaStream_t);
+// BINNED sort mode (preprocess.cu: count / scan / scatter; binsort.cu: per-bin segment sort)
+constexpr int BIN_CAP_XS = 2560, BIN_CAP_S = 5376, BIN_CAP_L = 11008;  // entries a bin of the class holds in shared memory
+constexpr int BIN_CLASSES = 4;
+struct BinSortWork {
+  uint32_t* class_list;   // [BIN_CLASSES][bins] bin ids per size class
+  uint32_t* class_count;  // [BIN_CLASSES]
+  uint32_t* class_next;   // [BIN_CLASSES] dynamic fetch counters
+};
+cudaError_t launch_bin_sort(uint2* entries, uint2* entries_tmp, uint32_t* rank_tmp, const uint2* ranges, uint32_t* vals_out,
+                            const BinSortWork& w, int bins, const uint32_t* overflow, int sm_count, cudaStream_t);
+// scan of per-bin counts -> ranges, cursors, size-class lists, pair total (+ overflow flag, host status word)
+cudaError_t launch_bin_scan(const uint32_t* bin_count, int bins, uint2* ranges, uint32_t* cursor, const BinSortWork& w,
+                            B200sStatus* status, unsigned long long pair_capacity, unsigned long long* status_host, cudaStream_t);
 cudaError_t launch_composite_fwd(const CompArgs&, int tiles, int views, bool depth, bool count, cudaStream_t);
 cudaError_t launch_composite_bwd(const CompArgs&, int tiles, int views, bool depth, cudaStream_t);
 cudaError_t launch_preprocess_bwd(const B200sScene&, const B200sViews&, const B200sPlan&, const char* saved, char* scratch,

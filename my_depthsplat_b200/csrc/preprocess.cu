@@ -45,6 +45,10 @@ struct PreArgs {
   B200sStatus* status;
   int32_t* radii;
   unsigned long long* status_host;  // mapped pinned host memory or NULL
+  // BINNED sort mode
+  uint32_t* bin_count;              // [bins] pairs per (view, tile) bin
+  uint32_t* bin_cursor;             // [bins] next free list position of every bin
+  uint2* entries;                   // [R_cap] (depth bits, Gaussian index), grouped by bin
 };
 
 constexpr uint64_t SCAN_FLAG_AGG = 1ull << 62, SCAN_FLAG_PREFIX = 2ull << 62, SCAN_VALUE_MASK = (1ull << 62) - 1;
@@ -395,10 +399,134 @@ __global__ void __launch_bounds__(PRE_THREADS) emit_kernel(const PreArgs a) {
   for (int p = 0; p < a.sort_passes; p++) { const uint32_t c = s_hist[p][tid]; if (c) atomicAdd(&a.hist[p * 256 + tid], c); }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// BINNED sort mode: the (tile, Gaussian) pairs go straight into their (view, tile) bin instead of through a global
+// sort.  bin_walk_kernel<false> counts the pairs of every bin, bin_scan_kernel turns the counts into the tile ranges
+// (which identifyTileRanges would find in the sorted keys) and bin_walk_kernel<true> writes every pair's
+// (depth bits, Gaussian index) entry at a position claimed from its bin's cursor; binsort.cu then orders each bin.
+// Both walks go over a warp's 32 Gaussians in lock step, tile by tile: pixel-aligned neighbours overlap the same tile, so
+// lanes are grouped into runs of equal bins and ONE atomic per run counts / claims for all of them (C2T: 34 M pairs,
+// ~7 M atomics).  A Gaussian covering more than BIG_RECT tiles is walked by the whole warp instead.
+constexpr uint32_t BIG_RECT = 32;
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(PRE_THREADS) bin_walk_kernel(const PreArgs a) {
+  if (SCATTER && a.status->overflow) return;  // the host re-runs with a larger capacity
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t le = 0xffffffffu >> (31 - lane);  // lanes <= mine
+  for (int ticket = blockIdx.x; ticket < a.n_tickets; ticket += gridDim.x) {
+    const int view = ticket % a.VV, chunk = ticket / a.VV;
+    const uint2 info = a.bin_info[(size_t)ticket * PRE_THREADS + tid];
+    const int rx0 = info.y & 255, ry0 = (info.y >> 8) & 255, rx1 = (info.y >> 16) & 255, ry1 = info.y >> 24;
+    const uint32_t tiles = (uint32_t)((rx1 - rx0) * (ry1 - ry0));
+    const uint32_t vhi = (uint32_t)view << a.tile_bits;
+    const uint2 entry = make_uint2(info.x, (uint32_t)(chunk * PRE_THREADS + tid));
+    const bool big = tiles > BIG_RECT;
+    const uint32_t steps = __reduce_max_sync(0xffffffffu, big ? 0u : tiles);
+    int x = rx0, y = ry0;
+    for (uint32_t t = 0; t < steps; t++) {
+      const bool act = !big && t < tiles;
+      const uint32_t bin = act ? (vhi | (uint32_t)(y * a.grid_x + x)) : 0xffffffffu;
+      const uint32_t prev = __shfl_up_sync(0xffffffffu, bin, 1);
+      const bool head = lane == 0 || prev != bin;
+      const uint32_t heads = __ballot_sync(0xffffffffu, head);
+      const int first = 31 - __clz(heads & le);                  // my run starts at the last head at or below me ...
+      const uint32_t above = heads & ~le;
+      const int end = above ? __ffs(above) - 1 : 32;             // ... and ends before the next head
+      if (SCATTER) {
+        uint32_t base = 0;
+        if (act && head) base = atomicAdd(&a.bin_cursor[bin], (uint32_t)(end - first));
+        base = __shfl_sync(0xffffffffu, base, first);
+        if (act) a.entries[base + (uint32_t)(lane - first)] = entry;
+      } else {
+        if (act && head) atomicAdd(&a.bin_count[bin], (uint32_t)(end - first));
+      }
+      if (act && ++x == rx1) { x = rx0; y++; }
+    }
+    uint32_t bmask = __ballot_sync(0xffffffffu, big);
+    while (bmask) {
+      const int src = __ffs(bmask) - 1;
+      bmask &= bmask - 1;
+      const int x0 = __shfl_sync(0xffffffffu, rx0, src), y0 = __shfl_sync(0xffffffffu, ry0, src);
+      const int w = __shfl_sync(0xffffffffu, rx1, src) - x0;
+      const uint32_t cnt = __shfl_sync(0xffffffffu, tiles, src);
+      const uint2 e = make_uint2(__shfl_sync(0xffffffffu, entry.x, src), __shfl_sync(0xffffffffu, entry.y, src));
+      for (uint32_t k = lane; k < cnt; k += 32) {
+        const int yy = y0 + (int)(k / (uint32_t)w), xx = x0 + (int)(k % (uint32_t)w);
+        const uint32_t bin = vhi | (uint32_t)(yy * a.grid_x + xx);
+        if (SCATTER) a.entries[atomicAdd(&a.bin_cursor[bin], 1u)] = e;
+        else atomicAdd(&a.bin_count[bin], 1u);
+      }
+    }
+  }
+}
+
+// One CTA: exclusive scan of the bin counts -> tile ranges and scatter cursors; bins sorted into the size classes of the
+// segment sort; pair total, overflow flag and longest bin into the status block and the host's status word.
+constexpr int BSCAN_THREADS = 1024;
+__global__ void __launch_bounds__(BSCAN_THREADS) bin_scan_kernel(const uint32_t* __restrict__ bin_count, int bins, uint2* __restrict__ ranges,
+                                                                 uint32_t* __restrict__ cursor, const BinSortWork w, B200sStatus* status,
+                                                                 unsigned long long pair_capacity, unsigned long long* status_host) {
+  __shared__ unsigned long long s_wsum[BSCAN_THREADS / 32];
+  __shared__ uint32_t s_cls[BIN_CLASSES];
+  __shared__ uint32_t s_max;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < BIN_CLASSES) s_cls[tid] = 0;
+  if (tid == 0) s_max = 0;
+  const int per = (bins + BSCAN_THREADS - 1) / BSCAN_THREADS;
+  const int b0 = min(bins, tid * per), b1 = min(bins, b0 + per);
+  unsigned long long tsum = 0;
+  uint32_t tmax = 0;
+  for (int b = b0; b < b1; b++) { const uint32_t c = bin_count[b]; tsum += c; tmax = max(tmax, c); }
+  unsigned long long incl = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) s_wsum[warp] = incl;
+  tmax = __reduce_max_sync(0xffffffffu, tmax);
+  __syncthreads();
+  if (lane == 0 && tmax) atomicMax(&s_max, tmax);
+  unsigned long long wexcl = 0, total = 0;
+#pragma unroll 4
+  for (int k = 0; k < BSCAN_THREADS / 32; k++) { const unsigned long long t = s_wsum[k]; if (k < warp) wexcl += t; total += t; }
+  unsigned long long run = wexcl + incl - tsum;
+  for (int b = b0; b < b1; b++) {
+    const uint32_t c = bin_count[b];
+    const uint32_t start = (uint32_t)run;  // list positions are 32-bit (pair_capacity < 2^32)
+    ranges[b] = make_uint2(start, start + c);
+    cursor[b] = start;
+    run += c;
+    if (c) {
+      const int cls = c <= (uint32_t)BIN_CAP_XS ? 0 : (c <= (uint32_t)BIN_CAP_S ? 1 : (c <= (uint32_t)BIN_CAP_L ? 2 : 3));
+      w.class_list[(size_t)cls * bins + atomicAdd(&s_cls[cls], 1u)] = (uint32_t)b;
+    }
+  }
+  __syncthreads();
+  if (tid < BIN_CLASSES) { w.class_count[tid] = s_cls[tid]; w.class_next[tid] = 0; }
+  if (tid == 0) {
+    const uint32_t over = total > pair_capacity ? 1u : 0u;
+    status->num_pairs = total;
+    status->overflow = over;
+    status->max_bin_len = s_max;
+    if (status_host) {  // straight to the host over PCIe: no copy engine, no extra launch
+      status_host[0] = total;
+      status_host[1] = (unsigned long long)over | ((unsigned long long)(0x80000000u | s_max) << 32);
+      __threadfence_system();
+    }
+  }
+}
+
 }  // namespace b200s
 
 // ---- host launcher (called from api.cu) --------------------------------------------------------
 namespace b200s {
+cudaError_t launch_bin_scan(const uint32_t* bin_count, int bins, uint2* ranges, uint32_t* cursor, const BinSortWork& w, B200sStatus* status,
+                            unsigned long long pair_capacity, unsigned long long* status_host, cudaStream_t stream) {
+  bin_scan_kernel<<<1, BSCAN_THREADS, 0, stream>>>(bin_count, bins, ranges, cursor, w, status, pair_capacity, status_host);
+  count_launches(1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, const B200sPlan& plan, char* saved, char* scratch,
                                   const B200sOut* out, cudaStream_t stream) {
   PreArgs a;
@@ -426,6 +554,10 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   a.status = reinterpret_cast<B200sStatus*>(saved + plan.off_status);
   a.radii = out ? out->radii : nullptr;
   a.status_host = out ? reinterpret_cast<unsigned long long*>(out->status_host) : nullptr;
+  const bool binned = plan.sort_mode == B200S_SORT_BINNED;
+  a.bin_count = reinterpret_cast<uint32_t*>(scratch + plan.off_bin_count);
+  a.bin_cursor = reinterpret_cast<uint32_t*>(scratch + plan.off_bin_cursor);
+  a.entries = reinterpret_cast<uint2*>(scratch + plan.off_keys_a);
 
   cudaError_t e;
   stage_mark(B200S_STAGE_PRE_BIN, stream);
@@ -433,27 +565,38 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   if ((e = cudaMemsetAsync(a.counters, 0, CNT_WORDS * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   const int scan_blocks = (plan.pre_tickets + SCAN_TILE - 1) / SCAN_TILE;
   if ((e = cudaMemsetAsync(a.scan_blocks, 0, (size_t)scan_blocks * sizeof(uint64_t), stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(a.hist, 0, 8 * 256 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+  if (binned) { if ((e = cudaMemsetAsync(a.bin_count, 0, (size_t)plan.bins * sizeof(uint32_t), stream)) != cudaSuccess) return e; }
+  else if ((e = cudaMemsetAsync(a.hist, 0, 8 * 256 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   const size_t smem = (size_t)PRE_THREADS * a.fpg * sizeof(float) + (size_t)PRE_THREADS * sizeof(Rec);
   const bool specialised = sc.cov_layout == B200S_COV_3X3 && !sc.colors_precomp && sc.sh_layout == B200S_SH_CHANNEL_MAJOR &&
                            sc.sh_coeffs == 9 && sc.sh_degree == 2;
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    if ((e = cudaFuncSetAttribute(project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    configured = smem;
+  // the attribute is per (function, device) and cheap to set: no cache that a second device or thread could get wrong
+  if (smem > 48 * 1024) {
+    if ((e = cudaFuncSetAttribute(specialised ? (const void*)project_kernel<true> : (const void*)project_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   }
   if (plan.pre_tickets > 0) {
     const int proj_blocks = a.chunks * sc.num_scenes;
     if (specialised) project_kernel<true><<<proj_blocks, PRE_THREADS, smem, stream>>>(sc, vw, a);
     else project_kernel<false><<<proj_blocks, PRE_THREADS, smem, stream>>>(sc, vw, a);
-    scan_kernel<<<scan_blocks, SCAN_THREADS, 0, stream>>>(a);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int emit_blocks = plan.pre_tickets < sms * 6 ? plan.pre_tickets : sms * 6;
-    emit_kernel<<<emit_blocks, PRE_THREADS, 0, stream>>>(a);
-    count_launches(3);
+    const int sms = device_sm_count();
+    const int walk_blocks = plan.pre_tickets < sms * 8 ? plan.pre_tickets : sms * 8;
+    if (binned) {
+      bin_walk_kernel<false><<<walk_blocks, PRE_THREADS, 0, stream>>>(a);
+      BinSortWork w;
+      w.class_list = reinterpret_cast<uint32_t*>(scratch + plan.off_long_list);
+      w.class_count = a.counters + CNT_BIN_CLASS_COUNT;
+      w.class_next = a.counters + CNT_BIN_CLASS_NEXT;
+      bin_scan_kernel<<<1, BSCAN_THREADS, 0, stream>>>(a.bin_count, plan.bins, reinterpret_cast<uint2*>(saved + plan.off_ranges), a.bin_cursor, w,
+                                                      a.status, a.pair_capacity, a.status_host);
+      bin_walk_kernel<true><<<walk_blocks, PRE_THREADS, 0, stream>>>(a);
+      count_launches(4);
+    } else {
+      scan_kernel<<<scan_blocks, SCAN_THREADS, 0, stream>>>(a);
+      const int emit_blocks = plan.pre_tickets < sms * 6 ? plan.pre_tickets : sms * 6;
+      emit_kernel<<<emit_blocks, PRE_THREADS, 0, stream>>>(a);
+      count_launches(3);
+    }
   }
   return cudaGetLastError();
 }

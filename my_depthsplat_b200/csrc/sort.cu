@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
 }
 
 // run-time tuning knobs (b200s_debug_set): [0] histogram variant, [1] ranking variant
-int g_sort_knobs[4] = {2, 2, 0, 0};
+std::atomic<int> g_sort_knobs[4] = {{2}, {2}, {0}, {0}};
 
 // ---------------------------------------------------------------------------------------------
 // HMODE 0/1: warp-aggregated by digit match (ballots / MATCH.ANY), plain read-modify-write by the group
@@ -331,12 +331,12 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
   uint64_t* kout = start_in_a ? keys_b : keys_a; uint32_t* vout = start_in_a ? vals_b : vals_a;
   {
     const size_t smem = (size_t)SORT_WARPS * passes * RADIX * sizeof(uint32_t);
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
+    static std::atomic<unsigned long long> hist_configured{0};
+    if (!hist_ready && smem > 48 * 1024) {  // per (function, device); only the stand-alone sort runs this kernel
       if ((e = cudaFuncSetAttribute(digit_histogram_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
       if ((e = cudaFuncSetAttribute(digit_histogram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
       if ((e = cudaFuncSetAttribute(digit_histogram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      configured = smem;
+      (void)hist_configured;
     }
     long long blocks = (n_cap + SORT_THREADS * 16 - 1) / (SORT_THREADS * 16);
     const long long max_blocks = (long long)sm_count * 4;
@@ -344,8 +344,8 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     if (blocks < 1) blocks = 1;
     stage_mark(B200S_STAGE_SORT_HIST, stream);
     if (!hist_ready) {  // forward computes the histograms while it emits the keys (emit_kernel); the stand-alone sort reads them here
-      if (g_sort_knobs[0] == 0) digit_histogram_kernel<0><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
-      else if (g_sort_knobs[0] == 1) digit_histogram_kernel<1><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+      if (g_sort_knobs[0].load(std::memory_order_relaxed) == 0) digit_histogram_kernel<0><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
+      else if (g_sort_knobs[0].load(std::memory_order_relaxed) == 1) digit_histogram_kernel<1><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
       else digit_histogram_kernel<2><<<(int)blocks, SORT_THREADS, smem, stream>>>(kin, cnt, hist, passes);
       count_launches(1);
     }
@@ -354,12 +354,11 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
   }
   stage_mark(B200S_STAGE_SORT_PASSES, stream);
   {
-    static thread_local bool sweep_configured = false;
-    if (!sweep_configured) {
+    static std::atomic<unsigned long long> sweep_configured{0};
+    if (first_use_on_device(sweep_configured)) {
       if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
       if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
       if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM)) != cudaSuccess) return e;
-      sweep_configured = true;
     }
   }
   for (int p = 0; p < passes; p++) {
@@ -371,8 +370,8 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
     a.tile_counter = counters + CNT_SORT_TILE0 + p;
     a.cnt = cnt; a.shift = 8 * p;
     const int nblk = tiles - 1 > 0 ? tiles - 1 : 1;
-    if (g_sort_knobs[1] == 0) onesweep_pass_kernel<0><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
-    else if (g_sort_knobs[1] == 1) onesweep_pass_kernel<1><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
+    if (g_sort_knobs[1].load(std::memory_order_relaxed) == 0) onesweep_pass_kernel<0><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
+    else if (g_sort_knobs[1].load(std::memory_order_relaxed) == 1) onesweep_pass_kernel<1><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
     else onesweep_pass_kernel<2><<<nblk, SORT_THREADS, SWEEP_SMEM, stream>>>(a);
     count_launches(1);
     uint64_t* tk = kin; kin = kout; kout = tk;

@@ -198,7 +198,7 @@ def render_views(
     bgs = (background_color, background_color) if background_color.dim() == 1 else (background_color[:, :half], background_color[:, half:])
     parts = [render_views(extrinsics[:, sl], intrinsics[:, sl], near[:, sl], far[:, sl], image_shape, bg, gaussian_means,
                           gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode,
-                          want_radii, count_work, None) for sl, bg in zip((slice(0, half), slice(half, V)), bgs)]
+                          want_radii, count_work, grad_reducer) for sl, bg in zip((slice(0, half), slice(half, V)), bgs)]
     out = [torch.cat([p[0] for p in parts], dim=1),
            None if parts[0][1] is None else torch.cat([p[1] for p in parts], dim=1)]
     if want_radii:

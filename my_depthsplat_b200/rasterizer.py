@@ -17,6 +17,7 @@ two Python threads rendering on the SAME stream at the same time are not support
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -56,6 +57,11 @@ class RenderStats:
     pair_capacity: int = 0
     retries: int = 0
 
+
+# "binned" (default): pairs scattered into their (view, tile) bin, one CTA orders each bin in shared memory;
+# "global": one onesweep radix sort over 64-bit (view | tile | depth) keys.  Same lists and ranges, bit for bit.
+sort_mode = os.environ.get("B200S_SORT_MODE", "binned")
+_SORT_MODES = {"binned": _lib.SORT_BINNED, "global": _lib.SORT_GLOBAL}
 
 _capacity_hint: dict = {}
 _scratch_cache: dict = {}
@@ -202,7 +208,7 @@ class _Rasterize(torch.autograd.Function):
         words = _status_ring.words
         retries = 0
         while True:
-            plan = _lib.plan(B, N, VV, H, W, cap)
+            plan = _lib.plan(B, N, VV, H, W, cap, _SORT_MODES[sort_mode])
             lease = _SavedLease(dev, plan.saved_bytes)
             saved = lease.tensor
             scratch = _scratch(dev, plan.scratch_bytes)

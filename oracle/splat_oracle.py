@@ -51,7 +51,7 @@ def lib() -> C.CDLL:
         for name in (
             "orc_out_color", "orc_radii", "orc_depths", "orc_xy", "orc_conic_opacity", "orc_rgb",
             "orc_clamped", "orc_tiles_touched", "orc_offsets", "orc_keys_unsorted", "orc_vals_unsorted",
-            "orc_keys", "orc_vals", "orc_ranges", "orc_final_T", "orc_n_contrib",
+            "orc_keys", "orc_vals", "orc_ranges", "orc_final_T", "orc_n_contrib", "orc_fragile",
         ):
             getattr(L, name).restype = vp
             getattr(L, name).argtypes = [vp]
@@ -103,6 +103,7 @@ class ViewState:
         self.ranges = _view(L.orc_ranges(handle), np.uint32, (gx * gy, 2))
         self.final_T = _view(L.orc_final_T(handle), np.float32, (H, W))
         self.n_contrib = _view(L.orc_n_contrib(handle), np.uint32, (H, W))
+        self.fragile = _view(L.orc_fragile(handle), np.uint8, (H, W))
 
     def close(self):
         if self._h:
@@ -162,5 +163,12 @@ def set_parallel_backward(on: bool) -> None:
     lib().orc_set_parallel_backward(1 if on else 0)
 
 
-def set_threads(n: int | None):
-    os.environ["OMP_NUM_THREADS"] = str(n or os.cpu_count())
+def set_threads(n: int | None = None) -> int:
+    """Size of the OpenMP team for the next calls (default: every core this process may run on).  Goes through
+    omp_set_num_threads, so it also works after libgomp was initialised with OMP_NUM_THREADS=1 (torchrun sets that)."""
+    L = lib()
+    L.orc_set_threads.restype = None
+    L.orc_set_threads.argtypes = [C.c_int]
+    L.orc_max_threads.restype = C.c_int
+    L.orc_set_threads(int(n or len(os.sched_getaffinity(0))))
+    return int(L.orc_max_threads())

@@ -147,7 +147,9 @@ def test_plan_regions_are_disjoint_aligned_and_in_bounds():
         if (H + 15) // 16 > 255 or (W + 15) // 16 > 255:
             continue
         cap = rnd.randint(1, 1 << rnd.randint(4, 31))
-        p = _lib.plan(B, N, VV, H, W, cap)
+        mode = rnd.choice([_lib.SORT_BINNED, _lib.SORT_GLOBAL])
+        p = _lib.plan(B, N, VV, H, W, cap, mode)
+        assert p.sort_mode == mode
         tickets = p.pre_tickets
         assert tickets == VV * ((N + 255) // 256)
         sort_tiles = (cap + SORT_TILE - 1) // SORT_TILE + 1
@@ -155,10 +157,14 @@ def test_plan_regions_are_disjoint_aligned_and_in_bounds():
                  (p.off_final_T, VV * H * W * 4), (p.off_n_contrib, VV * H * W * 4)]
         scratch = [(p.off_keys_a, cap * 8), (p.off_keys_b, cap * 8), (p.off_vals_b, cap * 4), (p.off_scan_state, tickets * 8),
                    (p.off_ticket_totals, tickets * 4), (p.off_scan_blocks, (tickets // 2048 + 1) * 8), (p.off_bin_info, tickets * 256 * 8),
-                   (p.off_hist, 8 * 256 * 4), (p.off_lookback, 2 * sort_tiles * 256 * 8), (p.off_counters, 64 * 4)]
+                   (p.off_hist, 8 * 256 * 4), (p.off_counters, 64 * 4)]
+        if mode == _lib.SORT_GLOBAL:
+            scratch += [(p.off_lookback, 2 * sort_tiles * 256 * 8)]
+        else:  # per-bin counts, scatter cursors, the four size-class lists of the segment sort
+            scratch += [(p.off_bin_count, p.bins * 4), (p.off_bin_cursor, p.bins * 4), (p.off_long_list, 4 * p.bins * 4)]
         for regions, total in ((saved, p.saved_bytes), (scratch, p.scratch_bytes)):
             regions = sorted(regions)
             for (o, n), (o2, _) in zip(regions, regions[1:] + [(total, 0)]):
-                assert o % 256 == 0 and o + n <= o2, (B, N, VV, H, W, cap, o, n, o2)
+                assert o % 256 == 0 and o + n <= o2, (B, N, VV, H, W, cap, mode, o, n, o2)
         # the backward's gradient records reuse the scratch from its start
         assert p.off_grad_rec + VV * N * 48 <= p.scratch_bytes

@@ -14,7 +14,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import leaf_gaussians, oracle_decoder_forward, per_view_extension_inputs
+from helpers import (check_view_stages, cuda_leaf_gaussians, leaf_gaussians, oracle_decoder_forward, per_view_extension_inputs,
+                     render_cpu_cameras, stage_dump)
 from my_depthsplat_b200.scenes import make_scene
 
 pytestmark = pytest.mark.gpu
@@ -22,60 +23,15 @@ pytestmark = pytest.mark.gpu
 SCENES = ["tiny", "small", "small_trained", "small_stress", "ragged"]
 
 
-def _cuda_gaussians(scene):
-    from my_depthsplat_b200.types import Gaussians
-    g = scene.gaussians
-    mk = lambda t: t.detach().clone().cuda().requires_grad_()
-    return Gaussians(mk(g.means), mk(g.covariances), mk(g.harmonics), mk(g.opacities))
+_cuda_gaussians = cuda_leaf_gaussians
+_render_cpu_cameras = render_cpu_cameras
+_stage_dump = stage_dump
 
 
 def _render(scene, g, depth_mode=None, **kw):
     from my_depthsplat_b200.cuda_splatting import render_views
     return render_views(scene.extrinsics.cuda(), scene.intrinsics.cuda(), scene.near.cuda(), scene.far.cuda(), scene.image_shape,
                         scene.background.cuda(), g.means, g.covariances, g.harmonics, g.opacities, depth_mode=depth_mode, **kw)
-
-
-def _render_cpu_cameras(scene, g, depth_mode=None, **kw):
-    """Same call as _render, but the camera block (view / projection matrices, tanfov, scale) is built on
-    the CPU exactly as the oracle's inputs are, then moved to the GPU.  torch's CPU and CUDA ``inverse`` /
-    ``matmul`` differ in the last bits; bit-exactness of keys is a statement about the kernels given
-    IDENTICAL camera matrices (the boundary the extension sees), so the stage tests feed identical ones."""
-    from my_depthsplat_b200 import cuda_splatting as cs
-    from my_depthsplat_b200.rasterizer import ViewPack, rasterize
-    B, V = scene.extrinsics.shape[:2]
-    h, w = scene.image_shape
-    ext = scene.extrinsics.reshape(B * V, 4, 4).float()
-    near, far = scene.near.reshape(-1).float(), scene.far.reshape(-1).float()
-    daff, dclamp = cs._depth_block(ext, near, far) if depth_mode is not None else (None, None)
-    scale = 1 / near
-    ext = ext.clone()
-    ext[..., :3, 3] = ext[..., :3, 3] * scale[:, None]
-    fov_x, fov_y = cs.get_fov(scene.intrinsics.reshape(B * V, 3, 3).float()).unbind(-1)
-    view, full, campos, tanfov = cs._camera_block(ext, near * scale, far * scale, fov_x, fov_y, (0.5 * fov_x).tan(), (0.5 * fov_y).tan())
-    c = lambda t: None if t is None else t.contiguous().cuda()
-    pack = ViewPack(torch.arange(B, dtype=torch.int32).repeat_interleave(V).cuda(), c(view), c(full), c(campos), c(tanfov),
-                    c(scene.background.expand(B * V, 3)), h, w, c(torch.stack([scale, scale ** 2], -1)), depth_mode, c(daff), c(dclamp))
-    color, depth, radii = rasterize(g.means, g.covariances, g.harmonics, g.opacities, pack, want_radii=True, **kw)
-    return color.reshape(B, V, 3, h, w), (None if depth is None else depth.reshape(B, V, h, w)), radii.reshape(B, V, -1)
-
-
-def _stage_dump():
-    """Stage outputs of the last rasterizer call, as numpy."""
-    from my_depthsplat_b200 import rasterizer as R
-    d = R.debug_last
-    plan, saved, scratch = d["plan"], d["saved"], d["scratch"]
-    torch.cuda.synchronize()
-    VV, N, Rn = d["VV"], d["N"], d["num_pairs"]
-    sv = saved.cpu().numpy()
-    sc = scratch[: plan.off_vals_b].cpu().numpy()
-    rec = sv[plan.off_rec: plan.off_rec + VV * N * 64].view(np.float32).reshape(VV, N, 16)
-    keys = sc[plan.off_keys_a: plan.off_keys_a + Rn * 8].view(np.uint64)
-    vals = sv[plan.off_vals_a: plan.off_vals_a + Rn * 4].view(np.uint32)
-    ranges = sv[plan.off_ranges: plan.off_ranges + plan.bins * 8].view(np.uint32).reshape(plan.bins, 2)
-    HW = d["H"] * d["W"]
-    final_T = sv[plan.off_final_T: plan.off_final_T + VV * HW * 4].view(np.float32).reshape(VV, d["H"], d["W"])
-    n_contrib = sv[plan.off_n_contrib: plan.off_n_contrib + VV * HW * 4].view(np.uint32).reshape(VV, d["H"], d["W"])
-    return dict(plan=plan, rec=rec, keys=keys, vals=vals, ranges=ranges, final_T=final_T, n_contrib=n_contrib)
 
 
 @pytest.mark.parametrize("n,bits", [(1, 64), (31, 40), (4096, 47), (4097, 42), (100_003, 64), (1_000_000, 47), (3_000_001, 48)])
@@ -114,39 +70,45 @@ def test_stage_outputs_bit_exact(name):
         d = _stage_dump()
     finally:
         R.debug_keep = False
-    plan = d["plan"]
     B, V = scene.extrinsics.shape[:2]
     radii = radii.cpu().numpy()
-    tile_mask = np.uint64((1 << plan.tile_bits) - 1)
     for b in range(B):
         for v in range(V):
             vi = b * V + v
             st = so.forward_view(**per_view_extension_inputs(scene, b, v))
+            check_view_stages(d, vi, st, radii[b, v])
             rec = d["rec"][vi]
             vis = st.radii > 0
-            np.testing.assert_array_equal(radii[b, v], st.radii)
-            np.testing.assert_array_equal(rec[vis, 13].view(np.int32), st.radii[vis])
-            np.testing.assert_array_equal(rec[vis, 12].view(np.uint32), st.depths[vis].view(np.uint32))
-            np.testing.assert_array_equal(rec[vis, 0:2].view(np.uint32), st.xy[vis].view(np.uint32))
-            np.testing.assert_array_equal(rec[vis, 4:7].view(np.uint32), st.conic_opacity[vis, 0:3][:, [0, 1, 2]].view(np.uint32))
             np.testing.assert_allclose(rec[vis, 8:11], st.rgb[vis], atol=2e-6)
-            # this view's slice of the globally sorted list
-            hi = (d["keys"] >> np.uint64(32))
-            sel = (hi >> np.uint64(plan.tile_bits)) == np.uint64(vi)
-            k = d["keys"][sel]
-            k_view = ((k >> np.uint64(32)) & tile_mask) << np.uint64(32) | (k & np.uint64(0xFFFFFFFF))
-            assert k_view.shape[0] == st.num_rendered
-            np.testing.assert_array_equal(k_view, st.keys)
-            np.testing.assert_array_equal(d["vals"][sel], st.vals)
-            first = int(np.argmax(sel)) if sel.any() else 0
-            rg = d["ranges"][(vi << plan.tile_bits): (vi << plan.tile_bits) + plan.tiles].astype(np.int64)
-            nonempty = rg[:, 1] > rg[:, 0]
-            np.testing.assert_array_equal(nonempty, st.ranges[:, 1] > st.ranges[:, 0])
-            np.testing.assert_array_equal(rg[nonempty] - first, st.ranges[nonempty].astype(np.int64))
-            # image state
-            same = d["n_contrib"][vi] == st.n_contrib
-            assert same.mean() >= 0.999, same.mean()
-            np.testing.assert_allclose(d["final_T"][vi][same], st.final_T[same], atol=2e-6)
+            # image state: identical wherever no cut of the algorithm sat within a few ulp of its threshold
+            solid = st.fragile == 0
+            np.testing.assert_array_equal(d["n_contrib"][vi][solid], st.n_contrib[solid])
+            np.testing.assert_allclose(d["final_T"][vi][solid], st.final_T[solid], atol=2e-6)
+
+
+@pytest.mark.parametrize("mode", ["binned", "global"])
+def test_both_sort_modes_give_the_same_lists(mode):
+    """BINNED (per-bin shared-memory segment sort) and GLOBAL (onesweep over 64-bit keys) produce the same sorted Gaussian
+    indices and tile ranges, bit for bit, and the same image."""
+    from my_depthsplat_b200 import rasterizer as R
+    from oracle import splat_oracle as so
+    scene = make_scene("small_stress")
+    g = _cuda_gaussians(scene)
+    R.debug_keep = True
+    old = R.sort_mode
+    R.sort_mode = mode
+    try:
+        with torch.no_grad():
+            color, depth, radii = _render_cpu_cameras(scene, g)
+        d = _stage_dump()
+    finally:
+        R.debug_keep = False
+        R.sort_mode = old
+    assert (d["keys"] is not None) == (mode == "global")
+    radii = radii.cpu().numpy()
+    for v in range(scene.extrinsics.shape[1]):
+        st = so.forward_view(**per_view_extension_inputs(scene, 0, v))
+        check_view_stages(d, v, st, radii[0, v])
 
 
 @pytest.mark.parametrize("name", SCENES)
