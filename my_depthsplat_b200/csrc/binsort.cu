@@ -9,12 +9,14 @@
 // index (the global sort is stable and pairs are emitted in index order).  The scatter claims positions with atomics,
 // so the arrival order is arbitrary; the segment sort therefore orders by the pair (depth bits, index):
 //   1. load the bin, min / max of the depth bits -> b = significant bits of (depth - min);
-//   2. ceil(b / 8) stable LSD counting passes over 8-bit digits of (depth - min): each warp ranks a contiguous chunk
-//      (MATCH.ANY groups + one shared atomic per group give the stable rank inside the chunk), one block-wide scan of
-//      the [digit][warp] counters turns them into destinations, second sweep moves (key, index);
-//   3. equal-depth runs (rare: two Gaussians of a tile with the same float depth) are ordered by index: each member
-//      counts the smaller indices of its run.  A bin with a run longer than RUN_CAP is instead re-sorted with LSD
-//      passes over the index bits first (degenerate scenes: thousands of Gaussians at exactly the same depth);
+//   2. stable LSD counting passes over 8-bit digits of the TOP min(b, 16) bits of (depth - min) -- two passes for the
+//      b ~ 25 of real bins: each warp ranks a contiguous chunk (MATCH.ANY groups + one shared atomic per group give
+//      the stable rank inside the chunk), one block-wide scan of the [digit][warp] counters turns them into
+//      destinations, a second sweep moves (key, index);
+//   3. runs of equal top bits (a few entries: 4 400 depths over 65 536 intervals) are put into (depth, index) order in
+//      place: each member counts the smaller pairs of its run.  A bin with a run longer than RUN_CAP is instead sorted
+//      completely with LSD passes over the index bits and then all depth bits (crowded or degenerate bins: thousands of
+//      Gaussians within a few ulp of depth, or at exactly the same depth);
 //   4. write the indices.
 // Four size classes, one launch each (the class lists are built on the device by bin_scan_kernel, CTAs fetch bins
 // from them dynamically): XS / S / L keep (key, index) ping-pong buffers + 16-bit ranks in shared memory at 4 / 2 / 1
@@ -25,7 +27,7 @@
 namespace b200s {
 
 constexpr int BS_DIGITS = 256;
-constexpr int RUN_CAP = 32;
+constexpr int RUN_CAP = 64;  // longest run of equal sorted bits the rank fix-up takes
 
 struct BinSortArgs {
   uint2* entries;            // [R] (depth bits, Gaussian index), grouped by bin, arbitrary order inside a bin
@@ -93,6 +95,12 @@ __device__ __forceinline__ void scan_counters(uint32_t* hist, uint32_t* s_wtot) 
 }
 
 // One stable counting pass over the 8-bit digit `shift` of (key - sub) [ON_VAL: of (index - sub)].
+// Both sweeps go over a warp's chunk UNROLL x 32 elements at a time with the loads, matches, atomics and shuffles of the
+// UNROLL groups issued back to back: the chain load -> MATCH -> shared atomic -> shuffle -> store is ~10^2 cycles long
+// and a CTA has few warps, so the instruction-level parallelism of independent groups is what keeps the SM busy
+// (same-address shared atomics of one warp execute in program order, so the ranks stay stable).
+constexpr int BS_UNROLL = 4;
+
 template <int T, bool ON_VAL, class Store>
 __device__ __forceinline__ void radix_pass(Store& st, uint32_t n, uint32_t sub, int shift, uint32_t* hist, uint32_t* s_wtot) {
   constexpr int W = T / 32, STR = W + 1;
@@ -103,50 +111,77 @@ __device__ __forceinline__ void radix_pass(Store& st, uint32_t n, uint32_t sub, 
   const uint32_t chunk = ((n + W - 1) / W + 31u) & ~31u;
   const uint32_t lo = min(n, warp * chunk), hi = min(n, lo + chunk);
   uint32_t* col = hist + warp;
-  for (uint32_t base = lo; base < hi; base += 32) {
-    const uint32_t i = base + lane;
-    const bool valid = i < hi;
-    const uint32_t x = valid ? (ON_VAL ? st.val(i) : st.key(i)) : 0u;
-    const uint32_t d = valid ? ((x - sub) >> shift) & 255u : 256u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t r = 0;
-    if (valid && lane == leader) r = atomicAdd(col + d * STR, (uint32_t)__popc(peers));
-    r = __shfl_sync(0xffffffffu, r, leader);
-    if (valid) st.set_rank(i, r + __popc(peers & lt));
+  for (uint32_t base = lo; base < hi; base += 32 * BS_UNROLL) {
+    uint32_t d[BS_UNROLL], peers[BS_UNROLL], r[BS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BS_UNROLL; u++) {
+      const uint32_t i = base + 32 * u + lane;
+      const uint32_t x = i < hi ? (ON_VAL ? st.val(i) : st.key(i)) : 0u;
+      d[u] = i < hi ? ((x - sub) >> shift) & 255u : 256u;
+    }
+#pragma unroll
+    for (int u = 0; u < BS_UNROLL; u++) peers[u] = __match_any_sync(0xffffffffu, d[u]);
+#pragma unroll
+    for (int u = 0; u < BS_UNROLL; u++) {
+      r[u] = 0;
+      if (d[u] < 256u && lane == __ffs(peers[u]) - 1) r[u] = atomicAdd(col + d[u] * STR, (uint32_t)__popc(peers[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < BS_UNROLL; u++) {
+      const uint32_t i = base + 32 * u + lane;
+      const uint32_t rr = __shfl_sync(0xffffffffu, r[u], __ffs(peers[u]) - 1);
+      if (i < hi) st.set_rank(i, rr + __popc(peers[u] & lt));
+    }
   }
   __syncthreads();
   scan_counters<T>(hist, s_wtot);
   __syncthreads();
-  for (uint32_t base = lo; base < hi; base += 32) {
-    const uint32_t i = base + lane;
-    if (i < hi) {
-      const uint2 e = st.get(i);
-      const uint32_t d = (((ON_VAL ? e.y : e.x) - sub) >> shift) & 255u;
-      st.put(col[d * STR] + st.rank(i), e);
+  for (uint32_t base = lo; base < hi; base += 32 * BS_UNROLL) {
+    uint2 e[BS_UNROLL];
+    uint32_t dst[BS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BS_UNROLL; u++) {
+      const uint32_t i = base + 32 * u + lane;
+      if (i < hi) { e[u] = st.get(i); dst[u] = st.rank(i); }
+    }
+#pragma unroll
+    for (int u = 0; u < BS_UNROLL; u++) {
+      const uint32_t i = base + 32 * u + lane;
+      if (i < hi) dst[u] += col[((((ON_VAL ? e[u].y : e[u].x) - sub) >> shift) & 255u) * STR];
+    }
+#pragma unroll
+    for (int u = 0; u < BS_UNROLL; u++) {
+      const uint32_t i = base + 32 * u + lane;
+      if (i < hi) st.put(dst[u], e[u]);
     }
   }
   __syncthreads();
   st.swap();
 }
 
+// (key, index) order
+__device__ __forceinline__ bool pair_less(uint2 a, uint2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
+
 template <int T, class Store>
 __device__ __forceinline__ void sort_segment(Store& st, uint32_t n, uint32_t kmin, uint32_t kmax, uint32_t vmin, uint32_t vmax,
                                              uint32_t* hist, uint32_t* s_wtot, uint32_t* s_flag, uint32_t* __restrict__ out) {
   const int tid = threadIdx.x;
   const int kbits = 32 - __clz(kmax - kmin);  // __clz(0) = 32
-  for (int shift = 0; shift < kbits; shift += 8) radix_pass<T, false>(st, n, kmin, shift, hist, s_wtot);
-  // a run of RUN_CAP + 1 equal depths?
+  // Counting passes over the TOP min(kbits, 16) bits only: afterwards the entries are in order up to permutations inside
+  // runs of equal top bits -- a handful of entries each, unless thousands of depths crowd into one 2^low ulp interval --
+  // and every member of such a run finds its final place by counting the smaller (depth, index) pairs of its run.
+  const int low = kbits > 16 ? kbits - 16 : 0;
+  for (int shift = low; shift < kbits; shift += 8) radix_pass<T, false>(st, n, kmin, shift, hist, s_wtot);
   if (tid == 0) *s_flag = 0;
   __syncthreads();
   {
     bool lng = false;
-    for (uint32_t i = tid; i + RUN_CAP < n; i += T) lng |= st.key(i) == st.key(i + RUN_CAP);
+    for (uint32_t i = tid; i + RUN_CAP < n; i += T) lng |= ((st.key(i) - kmin) >> low) == ((st.key(i + RUN_CAP) - kmin) >> low);
     if (lng) *s_flag = 1;
   }
   __syncthreads();
   const bool long_run = *s_flag != 0;
-  if (long_run) {  // degenerate bin: order by (depth, index) with index passes first (LSD), then the depth passes again
+  if (long_run) {  // crowded or degenerate bin: the complete LSD order -- index passes, then every depth bit
     const int vbits = 32 - __clz(vmax - vmin);
     for (int shift = 0; shift < vbits; shift += 8) radix_pass<T, true>(st, n, vmin, shift, hist, s_wtot);
     for (int shift = 0; shift < kbits; shift += 8) radix_pass<T, false>(st, n, kmin, shift, hist, s_wtot);
@@ -155,11 +190,12 @@ __device__ __forceinline__ void sort_segment(Store& st, uint32_t n, uint32_t kmi
     const uint2 e = st.get(i);
     uint32_t pos = i;
     if (!long_run) {
-      const bool eq_prev = i > 0 && st.key(i - 1) == e.x, eq_next = i + 1 < n && st.key(i + 1) == e.x;
-      if (eq_prev || eq_next) {  // member of an equal-depth run: its place is the number of smaller indices in the run
+      const uint32_t top = (e.x - kmin) >> low;
+      const bool eq_prev = i > 0 && ((st.key(i - 1) - kmin) >> low) == top, eq_next = i + 1 < n && ((st.key(i + 1) - kmin) >> low) == top;
+      if (eq_prev || eq_next) {
         uint32_t s = i, t = i + 1, smaller = 0;
-        while (s > 0 && st.key(s - 1) == e.x) { s--; smaller += st.val(s) < e.y; }
-        while (t < n && st.key(t) == e.x) { smaller += st.val(t) < e.y; t++; }
+        while (s > 0) { const uint2 o = st.get(s - 1); if (((o.x - kmin) >> low) != top) break; s--; smaller += pair_less(o, e); }
+        while (t < n) { const uint2 o = st.get(t); if (((o.x - kmin) >> low) != top) break; smaller += pair_less(o, e); t++; }
         pos = s + smaller;
       }
     }

@@ -52,6 +52,16 @@ __device__ __forceinline__ bool subtile_hit(const float4 q0, const TileGeom& g) 
   return (q0.x + q0.z >= g.X0) && (q0.x - q0.z <= g.X1) && (q0.y + q0.w >= g.Y0) && (q0.y - q0.w <= g.Y1);
 }
 
+// exp(x) for x <= 0 as ONE MUFU.EX2 on x * log2(e): <= 2 ulp of the exponential plus the rounding of the product
+// (|x| <= 5.6 wherever alpha can reach 1/255, so <= 5e-7 relative in all) -- the same order as expf's own 1-2 ulp, at 2
+// instructions instead of 8.  Forward and backward BOTH use it: alpha, hence every alpha >= 1/255 and T' >= 1e-4 cut, is
+// the same number in the two passes by construction (the reference recomputes alpha with the same exp in both passes too).
+__device__ __forceinline__ float exp_neg(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+
 // A compacted hit as a warp keeps it in its private shared-memory slots: everything one entry needs behind ONE base
 // address (the loop index is warp-uniform, so the loads are broadcasts with immediate offsets).
 struct __align__(16) HitSlot {
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs 
         const float4 h1 = h->q1;
         const float dx = __fsub_rn(h->x, g.pfx), dy = __fsub_rn(h->y, g.pfy);
         const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
-        const float alpha = fminf(ALPHA_MAX, __fmul_rn(h1.w, expf(power)));
+        const float alpha = fminf(ALPHA_MAX, __fmul_rn(h1.w, exp_neg(power)));
         const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
         const bool reach = !done && power <= 0.0f && alpha >= ALPHA_MIN;
         const bool live = reach && !(test_T < T_MIN);
@@ -156,19 +166,23 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs 
 }
 
 // -------------------------------------------------------------------------------------------------
-// reduce-scatter butterfly: on entry every lane holds 32 partials v[0..31]; on exit lane l holds in
-// v[0] the sum over the warp of partial l.
-template <int STRIDE>
-__device__ __forceinline__ void butterfly_step(float* v, const uint32_t lane) {
-  const bool upper = (lane & STRIDE) != 0;
-#pragma unroll
-  for (int i = 0; i < STRIDE; i++) {
-    const float send = upper ? v[i] : v[i + STRIDE];
-    const float keep = upper ? v[i + STRIDE] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, STRIDE);
-  }
-}
-
+// Backward.  Per pixel and entry the walk computes only what depends on the pixel; what depends on the Gaussian is
+// accumulated by a lane that OWNS the Gaussian:
+//
+//   pixel side (lane = pixel, as in the forward): entries are compacted into a warp-private ring of hit slots; for a
+//     batch of up to 16 hits, in list order back to front, every lane replays alpha and T, carries the scalar image of
+//     the behind-colour recurrence, and writes just TWO numbers per (hit, pixel) into a 16 x 32 shared-memory matrix:
+//         q = G * dL/dalpha   (drives dL/dmean2D, dL/dconic, dL/dopacity)      w = alpha * T   (drives dL/dcolour)
+//   hit side (lane = hit h = lane & 15, pixel half = lane >> 4): reads its row of the matrix (16 pixels per lane,
+//     conflict-free: rows are padded to 33 words), rebuilds (dx, dy) of every pixel from its own centre, and sums the
+//     six moments of q and the four colour sums in REGISTERS; the two halves are combined with one shuffle per value and
+//     the hit's ten sums go out as ten REDs (five per half).
+//
+// This replaces the reduce-scatter butterfly of the previous version (three hits' 30 partial sums per pixel reduced
+// across the warp with 31 shuffles + 62 selects + 31 adds): the transposition now moves 2 values per (hit, pixel) instead
+// of reducing 10, and the moment arithmetic runs once per (hit, pixel) on the hit side instead of in every pixel lane
+// before the reduction.  Per processed hit: ~45 (pixel side) + ~19 (hit side) warp instructions against ~105.
+//
 // Per-pixel state of the reverse walk.  The reference recurrence keeps, per channel, the colour accumulated BEHIND the
 // current entry (accum = last_alpha * last_colour + (1 - last_alpha) * accum) and contracts it with dL/dpixel; the
 // contraction commutes with the recurrence, so only its scalar image is carried:
@@ -187,25 +201,21 @@ __device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP; the arg
   return r;
 }
 
-// One list entry on the warp's 32 pixels; writes this pixel's 10 partial gradients to out[0..9].
-// Returns (warp-uniform) whether ANY pixel of the warp received a contribution: a quarter of the entries
-// that pass the bounding-box cull touch no pixel that is still "alive" at that list position, and they are
-// dropped before the cross-lane reduction.  All 32 lanes must call.  Branch-free below the vote: a lane the entry
-// does not reach runs the same arithmetic with alpha = 0 (T, the weights and q come out unchanged / zero) and keeps
-// its recurrence state through selects.
+constexpr int BWD_BATCH = 16;   // hits per batch: the hit side maps lane -> (hit = lane & 15, pixel half = lane >> 4)
+constexpr int BWD_SLOTS = 48;   // hit slots per warp: up to 15 left over + the 32 of a new chunk
+constexpr int BWD_ROW = 33;     // padded row of the (hit, pixel) matrices
+
+// One list entry on the warp's 32 pixels: returns (warp-uniform) whether ANY pixel of the warp received a contribution --
+// a quarter of the entries that pass the bounding-box cull touch no pixel that is still "alive" at that list position;
+// they are dropped before anything is stored.  All 32 lanes must call.  Branch-free below the vote: a lane the entry does
+// not reach runs the same arithmetic with alpha = 0 (T and the recurrence state come out unchanged, q = w = 0).
 template <bool DEPTH>
-__device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, PixState<DEPTH>& s, const TileGeom& g, float* out) {
+__device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, PixState<DEPTH>& s, const TileGeom& g, float& q_out, float& w_out) {
   const float4 h1 = h->q1;
   const float dx = __fsub_rn(h->x, g.pfx), dy = __fsub_rn(h->y, g.pfy);
   const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
-  // ex2.approx (2 instructions, <= 2e-6 relative for the powers that can be live) instead of expf's 8: the backward
-  // is held to 1e-4 of the gradient scale, not to the forward's 1e-5 on the image
-  float G = __expf(power);
-  float araw = __fmul_rn(h1.w, G);
-  // the alpha >= 1/255 cut must fall exactly where the forward put it (same expf, same rounding): the approximate
-  // exponential is off by up to ~1e-6 relative, so within 1e-5 of the threshold the decision is retaken with expf
-  // (a handful of (pixel, entry) pairs per image take this branch)
-  if (fabsf(__fmaf_rn(araw, 255.0f, -1.0f)) < 1e-5f) { G = expf(power); araw = __fmul_rn(h1.w, G); }
+  const float G = exp_neg(power);  // the forward's alpha, bit for bit: the cuts fall where the forward put them
+  const float araw = __fmul_rn(h1.w, G);
   const float alpha = fminf(ALPHA_MAX, araw);
   const bool live = h->pos < s.last_contributor && power <= 0.0f && alpha >= ALPHA_MIN;
   if (!__any_sync(0xffffffffu, live)) return false;
@@ -213,32 +223,21 @@ __device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, PixStat
   const float a_eff = live ? alpha : 0.f;
   const float inv = rcp_approx(1.f - a_eff);  // exactly 1 for a_eff = 0
   s.T = s.T * inv;
-  const float w = a_eff * s.T;
-  const float col[4] = {h2.x, h2.y, h2.z, h2.w};
-  float D = 0.f;
-#pragma unroll
-  for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) {
-    D += col[ch] * s.dpix[ch];
-    out[6 + ch] = w * s.dpix[ch];
-  }
-  if (!DEPTH) out[9] = 0.f;
+  w_out = a_eff * s.T;
+  float D = h2.x * s.dpix[0];
+  D = fmaf(h2.y, s.dpix[1], D);
+  D = fmaf(h2.z, s.dpix[2], D);
+  if (DEPTH) D = fmaf(h2.w, s.dpix[3], D);
   const float E = s.last_alpha * s.D_last + (1.f - s.last_alpha) * s.E;
   s.E = live ? E : s.E;
   s.D_last = live ? D : s.D_last;
   s.last_alpha = live ? alpha : s.last_alpha;
   const float dL_dalpha = (D - E) * s.T - s.tb * inv;
-  // moments of q = G * dL/dalpha over the pixels; the per-Gaussian factors (opacity, conic, half extent of the
-  // image, -1/2) are applied once per (view, Gaussian) by the projection backward instead of once per pixel:
+  // q = G * dL/dalpha; the per-Gaussian factors (opacity, conic, half extent of the image, -1/2) are applied once per
+  // (view, Gaussian) by the projection backward:
   //   dL/dmean2D = opacity * half * (-A*S_x - B*S_y, -C*S_y - B*S_x),  dL/dconic = -opacity/2 * (S_xx, S_xy, S_yy),
-  //   dL/dopacity = S_1
-  const float q = live ? G * dL_dalpha : 0.f;
-  const float qx = q * dx, qy = q * dy;
-  out[0] = qx;
-  out[1] = qy;
-  out[2] = qx * dx;
-  out[3] = qx * dy;
-  out[4] = qy * dy;
-  out[5] = q;
+  //   dL/dopacity = S_1,   S_f = sum over pixels of q * f(dx, dy)
+  q_out = live ? G * dL_dalpha : 0.f;
   return true;
 }
 
@@ -246,7 +245,10 @@ __device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, PixStat
 // where the register file holds fewer whole tiles)
 template <bool DEPTH, int CTA_WARPS, int MIN_CTAS>
 __global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel(const CompArgs a) {
-  __shared__ HitSlot s_slot[CTA_WARPS][32];
+  __shared__ HitSlot s_slot[CTA_WARPS][BWD_SLOTS];
+  __shared__ float s_q[CTA_WARPS][BWD_BATCH * BWD_ROW];
+  __shared__ float s_w[CTA_WARPS][BWD_BATCH * BWD_ROW];
+  __shared__ float4 s_dpix[CTA_WARPS][32];
   if (*a.overflow) return;
   constexpr int PER_TILE = 8 / CTA_WARPS;  // CTAs per tile
   const int tile = blockIdx.x / PER_TILE, view = blockIdx.y;
@@ -260,9 +262,7 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel
   const uint32_t* __restrict__ list = a.vals + range.x;
   const size_t HW = (size_t)a.H * a.W;
   const size_t pid = (size_t)g.py * a.W + g.px;
-  // after the reduction lane l holds value l of the batch: component c of entry e = l / 10
-  const int red_e = lane / 10, red_c = lane - 10 * red_e;
-  float* __restrict__ grec_lane = a.grad_rec + (size_t)view * a.N * GREC_FLOATS + red_c;
+  float* __restrict__ grec = a.grad_rec + (size_t)view * a.N * GREC_FLOATS;
 
   PixState<DEPTH> s;
   s.T = g.inside ? a.final_T[(size_t)view * HW + pid] : 0.f;
@@ -286,9 +286,71 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel
   for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
   if (wmax == 0) return;
 
+  HitSlot* const slots = s_slot[warp];
+  float* const mq = s_q[warp];
+  float* const mw = s_w[warp];
+  s_dpix[warp][lane] = make_float4(s.dpix[0], s.dpix[1], s.dpix[2], DEPTH ? s.dpix[3] : 0.f);
+  // hit-side role of this lane: hit hh of the batch, pixels half * 16 .. half * 16 + 15 of the sub-tile
+  const int hh = lane & (BWD_BATCH - 1), half = lane >> 4;
+  const float hx0 = g.X0, hy0 = g.Y0 + (float)(2 * half);  // pixel j of the half sits at (X0 + (j & 7), Y0 + 2 * half + (j >> 3))
+  const float* const mq_row = mq + hh * BWD_ROW + 16 * half;
+  const float* const mw_row = mw + hh * BWD_ROW + 16 * half;
+  const float4* const dp_half = s_dpix[warp] + 16 * half;
+  __syncwarp();
+
+  int cnt = 0;  // hits waiting in slots[0 .. cnt) (warp-uniform)
+
+  // one batch of nb <= 16 hits: slots[first .. first + nb)
+  auto run_batch = [&](const HitSlot* batch, const int nb) {
+    uint32_t nonempty = 0;
+#pragma unroll 4
+    for (int k = 0; k < nb; k++) {
+      float q, w;
+      if (!bwd_entry<DEPTH>(batch + k, s, g, q, w)) continue;
+      mq[k * BWD_ROW + lane] = q;
+      mw[k * BWD_ROW + lane] = w;
+      nonempty |= 1u << k;
+    }
+    if (nonempty) {
+      __syncwarp();
+      float S[10];
+#pragma unroll
+      for (int i = 0; i < 10; i++) S[i] = 0.f;
+      const bool mine = (nonempty >> hh) & 1u;
+      uint32_t gid = 0;
+      if (mine) {
+        const HitSlot* h = batch + hh;
+        const float bx = h->x, by = h->y;
+        gid = h->id;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const float q = mq_row[j], w = mw_row[j];
+          const float4 dp = dp_half[j];
+          const float dx = __fsub_rn(bx, hx0 + (float)(j & 7)), dy = __fsub_rn(by, hy0 + (float)(j >> 3));
+          const float qx = q * dx, qy = q * dy;
+          S[0] += qx; S[1] += qy;
+          S[2] = fmaf(qx, dx, S[2]); S[3] = fmaf(qx, dy, S[3]); S[4] = fmaf(qy, dy, S[4]);
+          S[5] += q;
+          S[6] = fmaf(w, dp.x, S[6]); S[7] = fmaf(w, dp.y, S[7]); S[8] = fmaf(w, dp.z, S[8]);
+          if (DEPTH) S[9] = fmaf(w, dp.w, S[9]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 10; i++) S[i] += __shfl_xor_sync(0xffffffffu, S[i], 16);
+      if (mine) {
+        float* dst = grec + (size_t)gid * GREC_FLOATS + 5 * half;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+          const float v = half ? S[5 + i] : S[i];
+          if (v != 0.f) atomicAdd(dst + i, v);
+        }
+      }
+      __syncwarp();  // the matrix rows are read before the next batch overwrites them
+    }
+  };
+
   // walk positions wmax-1 ... 0; lane l of a chunk starting at `top` holds position top-1-l, so that the
   // compacted slots ascend as the list is walked back to front
-  HitSlot* const slots = s_slot[warp];
   int top = (int)wmax;
   uint32_t id_cur = top - 1 - lane >= 0 ? __ldg(list + (top - 1 - lane)) : 0u;
   uint32_t id_nxt = top - 33 - lane >= 0 ? __ldg(list + (top - 33 - lane)) : 0u;
@@ -305,43 +367,33 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel
     const uint32_t mask = __ballot_sync(0xffffffffu, hit);
     if (mask == 0) continue;
     if (hit) {
-      HitSlot* d = slots + __popc(mask & lt);
+      HitSlot* d = slots + cnt + __popc(mask & lt);
       const float4* r = reinterpret_cast<const float4*>(vrec + id);
       d->q1 = __ldg(r + 1); d->q2 = __ldg(r + 2);
       d->x = q0.x; d->y = q0.y; d->pos = (uint32_t)pos; d->id = id;
     }
+    cnt += __popc(mask);
     __syncwarp();
-    const int nh = __popc(mask);
-    // batches of three NON-EMPTY entries: walk the compacted slots in order, keep an entry only if some pixel
-    // of the warp received a contribution from it (k and nh are warp-uniform: they live in uniform registers)
-    for (int k = 0; k < nh;) {
-      float v[32];
-      uint32_t id0 = 0xffffffffu, id1 = 0xffffffffu, id2 = 0xffffffffu;
-      bool f = false;
-      while (k < nh && !f) { f = bwd_entry<DEPTH>(slots + k, s, g, v); if (f) id0 = slots[k].id; k++; }
-      if (!f) break;
-      f = false;
-      while (k < nh && !f) { f = bwd_entry<DEPTH>(slots + k, s, g, v + 10); if (f) id1 = slots[k].id; k++; }
-      if (!f) {
-#pragma unroll
-        for (int i = 10; i < 20; i++) v[i] = 0.f;
+    if (cnt >= BWD_BATCH) {
+      int first = 0;
+      for (; cnt - first >= BWD_BATCH; first += BWD_BATCH) run_batch(slots + first, BWD_BATCH);
+      // the (< 16) hits left over move to the front of the buffer
+      const int left = cnt - first;
+      float4 t0, t1, t2;
+      if (lane < left) {
+        const float4* src = reinterpret_cast<const float4*>(slots + first + lane);
+        t0 = src[0]; t1 = src[1]; t2 = src[2];
       }
-      f = false;
-      while (k < nh && !f) { f = bwd_entry<DEPTH>(slots + k, s, g, v + 20); if (f) id2 = slots[k].id; k++; }
-      if (!f) {
-#pragma unroll
-        for (int i = 20; i < 30; i++) v[i] = 0.f;
+      __syncwarp();
+      if (lane < left) {
+        float4* dst = reinterpret_cast<float4*>(slots + lane);
+        dst[0] = t0; dst[1] = t1; dst[2] = t2;
       }
-      v[30] = 0.f; v[31] = 0.f;
-      butterfly_step<16>(v, lane); butterfly_step<8>(v, lane); butterfly_step<4>(v, lane);
-      butterfly_step<2>(v, lane); butterfly_step<1>(v, lane);
-      uint32_t gid = red_e == 0 ? id0 : id1;
-      gid = red_e == 2 ? id2 : gid;
-      gid = red_e > 2 ? 0xffffffffu : gid;
-      if (gid != 0xffffffffu && v[0] != 0.f) atomicAdd(grec_lane + (size_t)gid * GREC_FLOATS, v[0]);
+      cnt = left;
+      __syncwarp();
     }
-    __syncwarp();  // slot reads of this chunk are done before the next chunk overwrites them
   }
+  if (cnt > 0) run_batch(slots, cnt);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -359,18 +411,10 @@ cudaError_t launch_composite_bwd(const CompArgs& a, int tiles, int views, bool d
   dim3 grid(tiles, views);
   stage_mark(B200S_STAGE_COMP_BWD, stream);
   count_launches(1);
-  // Two CTAs of four warps per tile, seven per SM (72 registers, 28 warps): 2.39 ms against 2.43 ms for one eight-warp
-  // CTA per tile at three per SM (76 registers, 24 warps); four two-warp CTAs per tile measure the same as two four-warp
-  // ones; capping the eight-warp kernel at 64 registers for four per SM spills and is slower (2.71 ms).
-  // b200s_debug_set(2, 2) selects the eight-warp shape for A/B runs.
-  if (g_sort_knobs[2].load(std::memory_order_relaxed) == 2) {
-    if (depth) composite_bwd_kernel<true, 8, 3><<<grid, TILE_PIX, 0, stream>>>(a);
-    else composite_bwd_kernel<false, 8, 3><<<grid, TILE_PIX, 0, stream>>>(a);
-  } else {
-    dim3 g2(tiles * 2, views);
-    if (depth) composite_bwd_kernel<true, 4, 7><<<g2, 128, 0, stream>>>(a);
-    else composite_bwd_kernel<false, 4, 7><<<g2, 128, 0, stream>>>(a);
-  }
+  // Two CTAs of four warps per tile, seven per SM (72 registers, 28 KB of shared memory: 28 warps per SM)
+  dim3 g2(tiles * 2, views);
+  if (depth) composite_bwd_kernel<true, 4, 7><<<g2, 128, 0, stream>>>(a);
+  else composite_bwd_kernel<false, 4, 7><<<g2, 128, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -409,9 +409,10 @@ __global__ void __launch_bounds__(PRE_THREADS) emit_kernel(const PreArgs a) {
 // lanes are grouped into runs of equal bins and ONE atomic per run counts / claims for all of them (C2T: 34 M pairs,
 // ~7 M atomics).  A Gaussian covering more than BIG_RECT tiles is walked by the whole warp instead.
 constexpr uint32_t BIG_RECT = 32;
+constexpr int WALK_ILP = 4;
 
 template <bool SCATTER>
-__global__ void __launch_bounds__(PRE_THREADS) bin_walk_kernel(const PreArgs a) {
+__global__ void __launch_bounds__(PRE_THREADS, 6) bin_walk_kernel(const PreArgs a) {
   if (SCATTER && a.status->overflow) return;  // the host re-runs with a larger capacity
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t le = 0xffffffffu >> (31 - lane);  // lanes <= mine
@@ -425,24 +426,39 @@ __global__ void __launch_bounds__(PRE_THREADS) bin_walk_kernel(const PreArgs a) 
     const bool big = tiles > BIG_RECT;
     const uint32_t steps = __reduce_max_sync(0xffffffffu, big ? 0u : tiles);
     int x = rx0, y = ry0;
-    for (uint32_t t = 0; t < steps; t++) {
-      const bool act = !big && t < tiles;
-      const uint32_t bin = act ? (vhi | (uint32_t)(y * a.grid_x + x)) : 0xffffffffu;
-      const uint32_t prev = __shfl_up_sync(0xffffffffu, bin, 1);
-      const bool head = lane == 0 || prev != bin;
-      const uint32_t heads = __ballot_sync(0xffffffffu, head);
-      const int first = 31 - __clz(heads & le);                  // my run starts at the last head at or below me ...
-      const uint32_t above = heads & ~le;
-      const int end = above ? __ffs(above) - 1 : 32;             // ... and ends before the next head
-      if (SCATTER) {
-        uint32_t base = 0;
-        if (act && head) base = atomicAdd(&a.bin_cursor[bin], (uint32_t)(end - first));
-        base = __shfl_sync(0xffffffffu, base, first);
-        if (act) a.entries[base + (uint32_t)(lane - first)] = entry;
-      } else {
-        if (act && head) atomicAdd(&a.bin_count[bin], (uint32_t)(end - first));
+    // WALK_ILP steps per iteration, their atomics issued back to back: a claim is a round trip to L2, and the steps of a
+    // warp are independent of each other
+    for (uint32_t t0 = 0; t0 < steps; t0 += WALK_ILP) {
+      uint32_t bin[WALK_ILP], base[WALK_ILP];
+      int first[WALK_ILP], len[WALK_ILP];
+      bool act[WALK_ILP], head[WALK_ILP];
+#pragma unroll
+      for (int u = 0; u < WALK_ILP; u++) {
+        act[u] = !big && t0 + u < tiles;
+        bin[u] = act[u] ? (vhi | (uint32_t)(y * a.grid_x + x)) : 0xffffffffu;
+        if (act[u] && ++x == rx1) { x = rx0; y++; }
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, bin[u], 1);
+        head[u] = lane == 0 || prev != bin[u];
+        const uint32_t heads = __ballot_sync(0xffffffffu, head[u]);
+        first[u] = 31 - __clz(heads & le);                        // my run starts at the last head at or below me ...
+        const uint32_t above = heads & ~le;
+        len[u] = (above ? __ffs(above) - 1 : 32) - first[u];      // ... and ends before the next head
       }
-      if (act && ++x == rx1) { x = rx0; y++; }
+#pragma unroll
+      for (int u = 0; u < WALK_ILP; u++) {
+        base[u] = 0;
+        if (act[u] && head[u]) {
+          if (SCATTER) base[u] = atomicAdd(&a.bin_cursor[bin[u]], (uint32_t)len[u]);
+          else atomicAdd(&a.bin_count[bin[u]], (uint32_t)len[u]);
+        }
+      }
+      if (SCATTER) {
+#pragma unroll
+        for (int u = 0; u < WALK_ILP; u++) {
+          base[u] = __shfl_sync(0xffffffffu, base[u], first[u]);
+          if (act[u]) a.entries[base[u] + (uint32_t)(lane - first[u])] = entry;
+        }
+      }
     }
     uint32_t bmask = __ballot_sync(0xffffffffu, big);
     while (bmask) {

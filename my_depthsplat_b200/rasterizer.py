@@ -63,7 +63,62 @@ class RenderStats:
 sort_mode = os.environ.get("B200S_SORT_MODE", "binned")
 _SORT_MODES = {"binned": _lib.SORT_BINNED, "global": _lib.SORT_GLOBAL}
 
+# "event" (default): the host waits for stage A of every forward (pair count known, overflow repaired transparently);
+# "lazy": no host wait once a problem shape has been seen twice (see _Rasterize.forward)
+sync_policy = os.environ.get("B200S_SYNC", "event")
+
 _capacity_hint: dict = {}
+_max_pairs: dict = {}
+_seen: dict = {}
+_pending: list = []
+
+
+class PairCapacityOverflow(RuntimeError):
+    """Lazy mode only: a forward that had already returned ran out of pair capacity; its images are invalid."""
+
+
+def _note_pairs(key, num_pairs: int) -> None:
+    _capacity_hint[key] = min(max(int(num_pairs * 1.25) + 4096, 1 << 16), _PAIR_LIMIT)
+    _max_pairs[key] = max(_max_pairs.get(key, 0), num_pairs)
+    _seen[key] = _seen.get(key, 0) + 1
+
+
+class _Pending:
+    """A lazy-mode forward whose status word has not been looked at yet."""
+    __slots__ = ("ev", "slot", "key", "cap", "done")
+
+    def __init__(self, ev, slot, key, cap):
+        self.ev, self.slot, self.key, self.cap, self.done = ev, slot, key, cap, False
+
+    def check(self, block: bool) -> bool:
+        if self.done:
+            return True
+        if not block and not self.ev.query():
+            return False
+        self.ev.synchronize()
+        self.done = True
+        if self in _pending:
+            _pending.remove(self)
+        words = _status_ring.words
+        num_pairs, flags = int(words[2 * self.slot]), int(words[2 * self.slot + 1])
+        if not (flags >> 32):
+            raise RuntimeError("stage A did not report its pair count (status word not written)")
+        _note_pairs(self.key, num_pairs)
+        last_stats.num_pairs = num_pairs
+        if flags & 0xFFFFFFFF:
+            _seen[self.key] = 0  # back to the waiting protocol until the shape has settled again
+            raise PairCapacityOverflow(
+                f"a forward that had already returned needed {num_pairs} (tile, Gaussian) pairs but ran with a capacity of {self.cap}: "
+                "its images are invalid. rasterizer.sync_policy = 'event' repairs this transparently at the cost of one host wait per forward")
+        return True
+
+
+def _drain_pending(block: bool) -> None:
+    for p in list(_pending):
+        p.check(block)
+    # a status slot must not be handed out again while its call is still unchecked
+    while len(_pending) >= _HostStatusRing.SLOTS - 2:
+        _pending[0].check(True)
 _scratch_cache: dict = {}
 last_stats = RenderStats()
 # parity tests set debug_keep to look at the stage outputs (records, sorted keys, ranges) of the last call
@@ -186,6 +241,18 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, covs, colors, opacities, means2d, vp: ViewPack, use_sh: bool, sh_degree: int, sh_layout: int,
                 want_radii: bool, count_work: bool):
+        # the library launches on the CURRENT device: make it the tensors' device for the duration of the call
+        with torch.cuda.device(means.device):
+            return _Rasterize._forward(ctx, means, covs, colors, opacities, means2d, vp, use_sh, sh_degree, sh_layout, want_radii, count_work)
+
+    @staticmethod
+    def backward(ctx, g_color, g_depth, _g_radii):
+        with torch.cuda.device(ctx.saved_tensors[0].device):
+            return _Rasterize._backward(ctx, g_color, g_depth, _g_radii)
+
+    @staticmethod
+    def _forward(ctx, means, covs, colors, opacities, means2d, vp: ViewPack, use_sh: bool, sh_degree: int, sh_layout: int,
+                 want_radii: bool, count_work: bool):
         L = _lib.load()
         dev = means.device
         B, N = means.shape[0], means.shape[1]
@@ -203,8 +270,17 @@ class _Rasterize(torch.autograd.Function):
         out = _lib.Out(_ptr(color), _ptr(depth), _ptr(radii), 1 if count_work else 0, slot_ptr)
 
         key = (dev.index, B, N, VV, H, W)
-        cap = _capacity_hint.get(key) or max(4 * N * VV, 1 << 16)
-        cap = min(cap, _PAIR_LIMIT)
+        _drain_pending(block=False)
+        # "lazy": once this problem shape has been seen, do not wait for stage A at all -- run at twice the largest pair count
+        # seen so far and look at the status word later (next call, or this call's backward).  An overflow found that late
+        # cannot be repaired (the images were already handed out), so it raises; "event" (default) waits for stage A -- and
+        # for whatever the stream still had queued before it -- and re-runs the call transparently.
+        lazy = sync_policy == "lazy" and _seen.get(key, 0) >= 2 and not (debug_keep or count_work)
+        if lazy:
+            cap = min(max(2 * _max_pairs[key] + 4096, 1 << 16), _PAIR_LIMIT)
+        else:
+            cap = _capacity_hint.get(key) or max(4 * N * VV, 1 << 16)
+            cap = min(cap, _PAIR_LIMIT)
         words = _status_ring.words
         retries = 0
         while True:
@@ -217,9 +293,15 @@ class _Rasterize(torch.autograd.Function):
             # stage A wrote the pair count straight into mapped host memory; the event marks its end, and the
             # GPU already sorts and composites (speculatively, at this capacity) while the host looks at it
             ev = torch.cuda.Event()
-            ev.record()
+            ev.record(torch.cuda.current_stream(dev))
             _lib.check(L.b200s_forward_render(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(),
                                               C.byref(out), stream), "b200s_forward_render")
+            if lazy:
+                pending = _Pending(ev, slot, key, cap)
+                _pending.append(pending)
+                num_pairs = -1
+                break
+            pending = None
             ev.synchronize()
             num_pairs = int(words[2 * slot])
             flags = int(words[2 * slot + 1])
@@ -234,7 +316,8 @@ class _Rasterize(torch.autograd.Function):
                 raise PairLimitExceeded(f"{num_pairs} (tile, Gaussian) pairs in one call exceed the 2^32 limit; render fewer views per call")
             cap = min(int(num_pairs * 1.25) + 4096, _PAIR_LIMIT)
             retries += 1
-        _capacity_hint[key] = min(max(int(num_pairs * 1.25) + 4096, 1 << 16), _PAIR_LIMIT)
+        if not lazy:
+            _note_pairs(key, num_pairs)
 
         st = last_stats
         st.num_pairs, st.pair_capacity, st.retries = num_pairs, cap, retries
@@ -248,7 +331,7 @@ class _Rasterize(torch.autograd.Function):
             global debug_last
             debug_last = dict(plan=plan, saved=saved, scratch=scratch, num_pairs=num_pairs, N=N, VV=VV, H=H, W=W)
         ctx.save_for_backward(means, covs, colors, opacities)
-        ctx.b200 = (vp, use_sh, sh_degree, sh_layout, plan, lease, means2d is not None)
+        ctx.b200 = (vp, use_sh, sh_degree, sh_layout, plan, lease, means2d is not None, pending)
         outs = [color]
         if depth is not None:
             outs.append(depth)
@@ -261,10 +344,12 @@ class _Rasterize(torch.autograd.Function):
         return outs[0], outs[1], radii
 
     @staticmethod
-    def backward(ctx, g_color, g_depth, _g_radii):
+    def _backward(ctx, g_color, g_depth, _g_radii):
         L = _lib.load()
         means, covs, colors, opacities = ctx.saved_tensors
-        vp, use_sh, sh_degree, sh_layout, plan, lease, want_m2d = ctx.b200
+        vp, use_sh, sh_degree, sh_layout, plan, lease, want_m2d, pending = ctx.b200
+        if pending is not None:
+            pending.check(block=True)  # lazy mode: the forward's status word, normally long since written
         saved = lease.tensor
         dev = means.device
         VV, N = vp.scene_index.shape[0], means.shape[1]
