@@ -199,6 +199,7 @@ def run_ours(args):
     cfg = CONFIGS[args.config]
     V = args.views or cfg.v_tgt
     by_scene = args.shard == "scenes"
+    by_range = args.shard == "ranges" and world > 1
     if by_scene:
         # BASELINE config 4: the scenes of the batch are split over the ranks (args.scenes per GPU, all V views each);
         # every rank owns its scenes' Gaussians, so the rendering path needs no collective at all
@@ -210,9 +211,13 @@ def run_ours(args):
     H, W = scene_cpu.image_shape
     N = scene_cpu.gaussians.means.shape[1]
     g_ = scene_cpu.gaussians
+    # --shard ranges: every rank holds (host and device) only ITS contiguous range of the Gaussians -- what its share of the
+    # encoder produced; the ranks all-gather them over NVLink in the forward and reduce-scatter the gradients in the backward
+    from my_depthsplat_b200.dist import RangeShardedDecoder, range_bounds
+    gs = slice(*range_bounds(N, world, rank)) if by_range else slice(None)
     host = {
-        "means": g_.means[bs].contiguous(), "covariances": g_.covariances[bs].contiguous(),
-        "harmonics": g_.harmonics[bs].contiguous(), "opacities": g_.opacities[bs].contiguous(),
+        "means": g_.means[bs, gs].contiguous(), "covariances": g_.covariances[bs, gs].contiguous(),
+        "harmonics": g_.harmonics[bs, gs].contiguous(), "opacities": g_.opacities[bs, gs].contiguous(),
         # view sharding: cameras of ALL world*V target views (a few hundred bytes); my_depthsplat_b200.dist slices this rank's
         "extrinsics": scene_cpu.extrinsics[bs].contiguous(), "intrinsics": scene_cpu.intrinsics[bs].contiguous(),
         "near": scene_cpu.near[bs].contiguous(), "far": scene_cpu.far[bs].contiguous(),
@@ -224,7 +229,9 @@ def run_ours(args):
     dataset_cfg = type("DatasetCfg", (), {"background_color": [0.0, 0.0, 0.0]})()
     decoder = get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), dataset_cfg).to(dev)
     # view sharding + ONE NCCL all-reduce of the flattened per-Gaussian gradients in the backward (identity at N=1)
-    sharded = decoder if by_scene else ViewShardedDecoder(
+    full_dev = {k: getattr(g_, k)[bs].to(dev) for k in ("means", "covariances", "harmonics", "opacities")} if by_range else devt
+    ranged = RangeShardedDecoder(decoder, pieces=args.pieces, kernel_reduce=not args.nccl_scatter) if by_range else None
+    sharded = decoder if (by_scene or by_range) else ViewShardedDecoder(
         decoder, fused_reduce=(world > 1 and args.fused_reduce), overlap_reduce=(world > 1 and args.overlap_reduce),
         nvls_reduce=(world > 1 and args.nvls_reduce))
     if getattr(sharded, "reducer", None) is not None and hasattr(sharded.reducer, "chunks") and os.environ.get("B200S_REDUCE_CHUNKS"):
@@ -233,7 +240,10 @@ def run_ours(args):
 
     def step(t):
         leaves = [t[k].detach().requires_grad_() for k in gnames]
-        out = sharded.forward(Gaussians(*leaves), t["extrinsics"], t["intrinsics"], t["near"], t["far"], (H, W), depth_mode=None)
+        if by_range:
+            out = ranged.forward(Gaussians(*leaves), N, t["extrinsics"], t["intrinsics"], t["near"], t["far"], (H, W), depth_mode=None)
+        else:
+            out = sharded.forward(Gaussians(*leaves), t["extrinsics"], t["intrinsics"], t["near"], t["far"], (H, W), depth_mode=None)
         grads = torch.autograd.grad(out.color, leaves, t["grad_color"])
         return out.color, grads
 
@@ -366,7 +376,7 @@ def run_ours(args):
     from my_depthsplat_b200.cuda_splatting import render_views
     with torch.no_grad():
         render_views(*((devt[k] if by_scene else shard_views(devt[k], world, rank)) for k in ("extrinsics", "intrinsics", "near", "far")), (H, W), decoder.background_color,
-                     devt["means"], devt["covariances"], devt["harmonics"], devt["opacities"], count_work=True)
+                     full_dev["means"], full_dev["covariances"], full_dev["harmonics"], full_dev["opacities"], count_work=True)
     st = R.last_stats
     plan = _lib.plan(B_local, N, B_local * V, H, W, max(st.num_pairs, 1), R._SORT_MODES[R.sort_mode])
     binned = plan.sort_mode == _lib.SORT_BINNED
@@ -469,7 +479,10 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": _workload_name(cfg, scene_cpu, V), "views_per_gpu": V, "gaussians": N, "height": H, "width": W,
                        "l2": "inputs larger than L2 (Gaussians 472 MB + 64 B records per view)" if N * 160 > 126e6 else "inputs fit L2",
-                       "parallelism": (f"scene-sharded x{world}: {B_local} scene(s) per GPU, no collective on the rendering path") if by_scene else f"view-sharded x{world}, Gaussians replicated" + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
+                       "parallelism": (f"scene-sharded x{world}: {B_local} scene(s) per GPU, no collective on the rendering path") if by_scene else
+                       (f"view-sharded x{world}, Gaussians sharded by range ({N // world} per rank): NCCL all-gather over NVLink in the forward, "
+                        + ("NCCL reduce-scatter" if args.nccl_scatter else f"reduce-scatter by the library's NVLS kernel (multimem.ld_reduce) in {args.pieces} pieces under the projection backward")
+                        + " of the per-Gaussian gradients in the backward") if by_range else f"view-sharded x{world}, Gaussians replicated" + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
                                         else (", NCCL all-reduce of per-Gaussian grads" + (" in 2 chunks overlapped with the projection backward" if args.overlap_reduce else ""))) if world > 1 else "")},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_step_e, 4), "pinned_copy_bandwidth": pcie, "allocator_events": alloc_events,
@@ -499,7 +512,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2T")
     ap.add_argument("--views", type=int, default=0, help="target views per GPU (default: the config's)")
-    ap.add_argument("--shard", default="views", choices=["views", "scenes"],
+    ap.add_argument("--pieces", type=int, default=4, help="--shard ranges: pieces of the projection backward (one reduce-scatter pull each)")
+    ap.add_argument("--nccl-scatter", action="store_true", help="--shard ranges: NCCL reduce_scatter after the backward instead of the NVLS kernel")
+    ap.add_argument("--shard", default="views", choices=["views", "scenes", "ranges"],
                     help="N>1: split the target views of replicated scenes (default; gradients all-reduced) or the scenes of the "
                          "batch (config 4: no collective on this path)")
     ap.add_argument("--scenes", type=int, default=1, help="--shard scenes: scenes per GPU")

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 7
+#define B200S_ABI_VERSION 8
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -183,7 +183,18 @@ typedef struct B200sGradIn { /* all fp32, OVERWRITTEN (summed over the views of 
                              chunk's gradients across GPUs while the next chunk is computed. */
   int32_t chunk_begin;    /* projection backward: first 256-Gaussian chunk of every scene to process ... */
   int32_t chunk_count;    /* ... and how many (0 = all remaining) */
+  int32_t chunk_stride;   /* with chunk_repeat > 1 the launch covers the chunks chunk_begin + r * chunk_stride + k, r < chunk_repeat, */
+  int32_t chunk_repeat;   /* k < chunk_count (clipped to the scene): the j-th piece of EVERY rank's Gaussian range in one launch,
+                             so that all ranks can pull their share of it (reduce-scatter) while the next piece is computed */
 } B200sGradIn;
+
+/* Reduce-scatter building block over an NVSwitch domain: for each of the nseg (<= 16) segments -- seg_offset[i] floats into a
+ * SYMMETRIC buffer, seg_count[i] floats, both multiples of 4 -- the calling rank pulls the sum over all ranks' replicas
+ * (multimem.ld_reduce on the multicast address) and stores it into ITS OWN replica (local_base).  Nothing is sent to the
+ * other ranks: each rank calls this for the part of the gradients it owns.  The caller orders it after a cross-rank barrier
+ * (all replicas complete). */
+int b200s_nvls_reduce_segments(void* multicast_base, void* local_base, const unsigned long long* seg_offset,
+                               const unsigned long long* seg_count, int nseg, void* stream);
 
 /* Pure host function: fills the plan for the given dimensions.  No CUDA calls. */
 int b200s_plan(const B200sDims* dims, B200sPlan* plan);

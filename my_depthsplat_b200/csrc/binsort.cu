@@ -2,26 +2,30 @@
 // memory.  Together with the counting / scattering kernels of preprocess.cu this replaces
 // cub::DeviceRadixSort::SortPairs + identifyTileRanges behind _C.rasterize_gaussians: instead of
 // six global passes over 64-bit (view | tile | depth) keys (24 B of HBM traffic per pair per pass), the pairs are
-// scattered straight into their bin (8 B written), and each bin is read once (8 B) and its sorted Gaussian indices
-// written once (4 B).
+// scattered straight into their bin (8 B written), and each bin is read (8 B, twice more out of L2) and its sorted
+// Gaussian indices written once (4 B).
 //
 // Order inside a bin = the order the stable global sort produces: ascending depth bits, ties in ascending Gaussian
 // index (the global sort is stable and pairs are emitted in index order).  The scatter claims positions with atomics,
-// so the arrival order is arbitrary; the segment sort therefore orders by the pair (depth bits, index):
-//   1. load the bin, min / max of the depth bits -> b = significant bits of (depth - min);
-//   2. stable LSD counting passes over 8-bit digits of the TOP min(b, 16) bits of (depth - min) -- two passes for the
-//      b ~ 25 of real bins: each warp ranks a contiguous chunk (MATCH.ANY groups + one shared atomic per group give
-//      the stable rank inside the chunk), one block-wide scan of the [digit][warp] counters turns them into
-//      destinations, a second sweep moves (key, index);
-//   3. runs of equal top bits (a few entries: 4 400 depths over 65 536 intervals) are put into (depth, index) order in
-//      place: each member counts the smaller pairs of its run.  A bin with a run longer than RUN_CAP is instead sorted
-//      completely with LSD passes over the index bits and then all depth bits (crowded or degenerate bins: thousands of
-//      Gaussians within a few ulp of depth, or at exactly the same depth);
-//   4. write the indices.
-// Four size classes, one launch each (the class lists are built on the device by bin_scan_kernel, CTAs fetch bins
-// from them dynamically): XS / S / L keep (key, index) ping-pong buffers + 16-bit ranks in shared memory at 4 / 2 / 1
-// CTAs per SM; XL (longer than CAP_L) runs the same passes on ping-pong buffers in global memory (L2-resident for the
-// sizes that occur), so there is no limit on the bin length.
+// so the arrival order is arbitrary; the segment sort therefore orders by the pair (depth bits, index).
+//
+// bucket_sort_kernel (bins that fit shared memory: three size classes at 4 / 2 / 1 CTAs per SM):
+//   1. read the bin: min / max of the depth bits -> b = significant bits of (depth - min);
+//   2. ONE counting sort on the top ~log2(2n) (8..13) bits of (depth - min): read the bin again (L2), histogram with
+//      fire-and-forget shared atomics on 16-bit counters, one block-wide scan, read the bin a third time and place
+//      every entry at a position claimed from its bucket (arbitrary order inside a bucket);
+//   3. with about as many buckets as entries, a bucket holds a handful of entries (a tile's depths are spread over
+//      thousands of 2^low-ulp intervals), so every entry finds its final place by counting the smaller
+//      (depth, index) pairs of its own bucket, and writes its index there.
+//   That is ~2 warp instructions per entry; an LSD radix sort of the same keys needs ~10 (four passes of two sweeps).
+//   A bin where more than RUN_CAP entries crowd into one bucket (degenerate scenes: thousands of Gaussians within a few
+//   ulp of depth) is handed to the robust path below instead.
+// lsd_sort_kernel (bins longer than the largest shared-memory class, and crowded bins): stable LSD counting passes over
+//   8-bit digits of all significant depth bits on ping-pong buffers in global memory (L2-resident for the sizes that
+//   occur) -- each warp ranks a contiguous chunk with MATCH.ANY groups + one shared atomic per group, one block-wide
+//   scan of the [digit][warp] counters gives the destinations -- then exact-depth ties are ordered by index (rank
+//   inside the run; index passes first when a run is long).  No limit on the bin length.
+// The class lists are built on the device by bin_scan_kernel; CTAs fetch bins from them dynamically.
 #include "kernels.cuh"
 
 namespace b200s {
@@ -39,20 +43,11 @@ struct BinSortArgs {
   const uint32_t* count;     // how many
   uint32_t* next;            // dynamic fetch counter
   const uint32_t* overflow;
+  uint32_t* retry_list;      // bucket path: bins too crowded for it are appended to the LSD class's list ...
+  uint32_t* retry_count;     // ... by bumping its count
 };
 
-// ---- storage policies: where the (key, index) ping-pong and the ranks live -------------------------------------
-struct SmemStore {
-  uint32_t *kA, *vA, *kB, *vB;
-  uint16_t* rk;
-  __device__ __forceinline__ uint32_t key(uint32_t i) const { return kA[i]; }
-  __device__ __forceinline__ uint32_t val(uint32_t i) const { return vA[i]; }
-  __device__ __forceinline__ uint2 get(uint32_t i) const { return make_uint2(kA[i], vA[i]); }
-  __device__ __forceinline__ void put(uint32_t i, uint2 e) { kB[i] = e.x; vB[i] = e.y; }
-  __device__ __forceinline__ void set_rank(uint32_t i, uint32_t r) { rk[i] = (uint16_t)r; }
-  __device__ __forceinline__ uint32_t rank(uint32_t i) const { return rk[i]; }
-  __device__ __forceinline__ void swap() { uint32_t* t = kA; kA = kB; kB = t; t = vA; vA = vB; vB = t; }
-};
+// ---- the (key, index) ping-pong and the ranks of the LSD path live in global memory --------------------------------
 struct GmemStore {
   uint2 *A, *B;
   uint32_t* rk;
@@ -167,21 +162,18 @@ __device__ __forceinline__ void sort_segment(Store& st, uint32_t n, uint32_t kmi
                                              uint32_t* hist, uint32_t* s_wtot, uint32_t* s_flag, uint32_t* __restrict__ out) {
   const int tid = threadIdx.x;
   const int kbits = 32 - __clz(kmax - kmin);  // __clz(0) = 32
-  // Counting passes over the TOP min(kbits, 16) bits only: afterwards the entries are in order up to permutations inside
-  // runs of equal top bits -- a handful of entries each, unless thousands of depths crowd into one 2^low ulp interval --
-  // and every member of such a run finds its final place by counting the smaller (depth, index) pairs of its run.
-  const int low = kbits > 16 ? kbits - 16 : 0;
-  for (int shift = low; shift < kbits; shift += 8) radix_pass<T, false>(st, n, kmin, shift, hist, s_wtot);
+  for (int shift = 0; shift < kbits; shift += 8) radix_pass<T, false>(st, n, kmin, shift, hist, s_wtot);
+  // a run of more than RUN_CAP exactly equal depths?
   if (tid == 0) *s_flag = 0;
   __syncthreads();
   {
     bool lng = false;
-    for (uint32_t i = tid; i + RUN_CAP < n; i += T) lng |= ((st.key(i) - kmin) >> low) == ((st.key(i + RUN_CAP) - kmin) >> low);
+    for (uint32_t i = tid; i + RUN_CAP < n; i += T) lng |= st.key(i) == st.key(i + RUN_CAP);
     if (lng) *s_flag = 1;
   }
   __syncthreads();
   const bool long_run = *s_flag != 0;
-  if (long_run) {  // crowded or degenerate bin: the complete LSD order -- index passes, then every depth bit
+  if (long_run) {  // degenerate bin: the complete LSD order -- index passes, then the depth passes again
     const int vbits = 32 - __clz(vmax - vmin);
     for (int shift = 0; shift < vbits; shift += 8) radix_pass<T, true>(st, n, vmin, shift, hist, s_wtot);
     for (int shift = 0; shift < kbits; shift += 8) radix_pass<T, false>(st, n, kmin, shift, hist, s_wtot);
@@ -190,12 +182,11 @@ __device__ __forceinline__ void sort_segment(Store& st, uint32_t n, uint32_t kmi
     const uint2 e = st.get(i);
     uint32_t pos = i;
     if (!long_run) {
-      const uint32_t top = (e.x - kmin) >> low;
-      const bool eq_prev = i > 0 && ((st.key(i - 1) - kmin) >> low) == top, eq_next = i + 1 < n && ((st.key(i + 1) - kmin) >> low) == top;
-      if (eq_prev || eq_next) {
+      const bool eq_prev = i > 0 && st.key(i - 1) == e.x, eq_next = i + 1 < n && st.key(i + 1) == e.x;
+      if (eq_prev || eq_next) {  // member of an equal-depth run: its place is the number of smaller indices in the run
         uint32_t s = i, t = i + 1, smaller = 0;
-        while (s > 0) { const uint2 o = st.get(s - 1); if (((o.x - kmin) >> low) != top) break; s--; smaller += pair_less(o, e); }
-        while (t < n) { const uint2 o = st.get(t); if (((o.x - kmin) >> low) != top) break; smaller += pair_less(o, e); t++; }
+        while (s > 0 && st.key(s - 1) == e.x) { s--; smaller += st.val(s) < e.y; }
+        while (t < n && st.key(t) == e.x) { smaller += st.val(t) < e.y; t++; }
         pos = s + smaller;
       }
     }
@@ -209,16 +200,15 @@ __device__ __forceinline__ void block_minmax(uint32_t kmn, uint32_t kmx, uint32_
   if ((threadIdx.x & 31) == 0) { atomicMin(&s_mm[0], kmn); atomicMax(&s_mm[1], kmx); atomicMin(&s_mm[2], vmn); atomicMax(&s_mm[3], vmx); }
 }
 
-// XL = false: bins of at most CAP entries, ping-pong in shared memory; XL = true: any length, ping-pong in global memory
-template <int T, int CAP, int MIN_CTAS, bool XL>
-__global__ void __launch_bounds__(T, MIN_CTAS) bin_sort_kernel(const BinSortArgs a) {
+// ---- LSD path: any bin length, ping-pong in global memory -------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(T, 1) lsd_sort_kernel(const BinSortArgs a) {
   constexpr int W = T / 32, STR = W + 1;
-  extern __shared__ __align__(16) uint32_t bs_smem[];
+  __shared__ uint32_t hist[BS_DIGITS * STR];
   __shared__ uint32_t s_wtot[32];
   __shared__ uint32_t s_mm[4];
   __shared__ uint32_t s_flag, s_fetch;
   if (*a.overflow) return;
-  uint32_t* hist = bs_smem;  // [256][W + 1]
   const int tid = threadIdx.x;
   const uint32_t nbins = *a.count;
   for (;;) {
@@ -229,47 +219,149 @@ __global__ void __launch_bounds__(T, MIN_CTAS) bin_sort_kernel(const BinSortArgs
     const uint2 range = a.ranges[a.list[s_fetch]];
     const uint32_t n = range.y - range.x;
     uint32_t kmn = 0xffffffffu, kmx = 0u, vmn = 0xffffffffu, vmx = 0u;
-    if (XL) {
-      GmemStore st{a.entries + range.x, a.entries_tmp + range.x, a.rank_tmp + range.x};
-      for (uint32_t i = tid; i < n; i += T) {
-        const uint2 e = st.A[i];
-        kmn = min(kmn, e.x); kmx = max(kmx, e.x); vmn = min(vmn, e.y); vmx = max(vmx, e.y);
+    GmemStore st{a.entries + range.x, a.entries_tmp + range.x, a.rank_tmp + range.x};
+    for (uint32_t i = tid; i < n; i += T) {
+      const uint2 e = st.A[i];
+      kmn = min(kmn, e.x); kmx = max(kmx, e.x); vmn = min(vmn, e.y); vmx = max(vmx, e.y);
+    }
+    block_minmax(kmn, kmx, vmn, vmx, s_mm);
+    __syncthreads();
+    sort_segment<T>(st, n, s_mm[0], s_mm[1], s_mm[2], s_mm[3], hist, s_wtot, &s_flag, a.vals_out + range.x);
+  }
+}
+
+// ---- bucket path ---------------------------------------------------------------------------------------------------------
+constexpr int BK_MAX_BITS = 13;                       // at most 8192 buckets: 16-bit counters, two per word
+constexpr int BK_WORDS = (1 << BK_MAX_BITS) / 2;
+
+// exclusive scan of nb 16-bit counters packed two per word (nb a power of two >= 256); positions stay below 65536
+template <int T>
+__device__ __forceinline__ void scan_u16(uint32_t* h, int nb, uint32_t* s_wtot) {
+  constexpr int WPT = BK_WORDS / T > 0 ? BK_WORDS / T : 1;   // words per thread at the largest histogram
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int words = nb >> 1;
+  const int wpt = words / T > 0 ? words / T : 1;
+  const int w0 = tid * wpt;
+  uint32_t c[WPT], sum = 0;
+#pragma unroll
+  for (int j = 0; j < WPT; j++) {
+    c[j] = (j < wpt && w0 + j < words) ? h[w0 + j] : 0u;
+    sum += (c[j] & 0xffffu) + (c[j] >> 16);
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t t = lane < T / 32 ? s_wtot[lane] : 0u;
+    uint32_t x = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    s_wtot[lane] = x - t;
+  }
+  __syncthreads();
+  uint32_t run = s_wtot[warp] + incl - sum;
+#pragma unroll
+  for (int j = 0; j < WPT; j++) {
+    if (j < wpt && w0 + j < words) {
+      const uint32_t lo = c[j] & 0xffffu, hi = c[j] >> 16;
+      h[w0 + j] = run | ((run + lo) << 16);
+      run += lo + hi;
+    }
+  }
+}
+
+template <int T, int CAP, int MIN_CTAS>
+__global__ void __launch_bounds__(T, MIN_CTAS) bucket_sort_kernel(const BinSortArgs a) {
+  extern __shared__ __align__(16) uint32_t bs_smem[];
+  __shared__ uint32_t s_wtot[32];
+  __shared__ uint32_t s_mm[4];
+  __shared__ uint32_t s_flag, s_fetch;
+  if (*a.overflow) return;
+  uint32_t* hist = bs_smem;            // [BK_WORDS] two 16-bit bucket counters per word
+  uint32_t* kB = hist + BK_WORDS;      // [CAP] depth bits in bucket order
+  uint32_t* vB = kB + CAP;             // [CAP] Gaussian indices
+  const int tid = threadIdx.x;
+  const uint32_t nbins = *a.count;
+  for (;;) {
+    __syncthreads();  // the previous bin's readers of the shared state are done
+    if (tid == 0) { s_fetch = atomicAdd(a.next, 1u); s_mm[0] = 0xffffffffu; s_mm[1] = 0u; s_mm[2] = 0xffffffffu; s_mm[3] = 0u; s_flag = 0; }
+    __syncthreads();
+    if (s_fetch >= nbins) return;
+    const uint32_t bin = a.list[s_fetch];
+    const uint2 range = a.ranges[bin];
+    const uint32_t n = range.y - range.x;
+    const uint2* __restrict__ src = a.entries + range.x;
+    // bucket count ~ 2n .. 4n (256 .. 8192)
+    int bbits = 33 - __clz(n);
+    bbits = bbits < 8 ? 8 : (bbits > BK_MAX_BITS ? BK_MAX_BITS : bbits);
+    const int nb = 1 << bbits;
+    for (int i = tid; i < (nb >> 1); i += T) hist[i] = 0;
+    uint32_t kmn = 0xffffffffu, kmx = 0u;
+    for (uint32_t i = tid; i < n; i += T) { const uint32_t k = src[i].x; kmn = min(kmn, k); kmx = max(kmx, k); }
+    kmn = __reduce_min_sync(0xffffffffu, kmn); kmx = __reduce_max_sync(0xffffffffu, kmx);
+    if ((tid & 31) == 0) { atomicMin(&s_mm[0], kmn); atomicMax(&s_mm[1], kmx); }
+    __syncthreads();
+    const uint32_t kmin = s_mm[0];
+    const int kbits = 32 - __clz(s_mm[1] - kmin);
+    const int low = kbits > bbits ? kbits - bbits : 0;
+    for (uint32_t i = tid; i < n; i += T) {
+      const uint32_t b = (src[i].x - kmin) >> low;
+      atomicAdd(&hist[b >> 1], 1u << ((b & 1u) * 16));
+    }
+    __syncthreads();
+    scan_u16<T>(hist, nb, s_wtot);
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += T) {
+      const uint2 e = src[i];
+      const uint32_t b = (e.x - kmin) >> low, sh = (b & 1u) * 16;
+      const uint32_t pos = (atomicAdd(&hist[b >> 1], 1u << sh) >> sh) & 0xffffu;
+      kB[pos] = e.x; vB[pos] = e.y;
+    }
+    __syncthreads();
+    {  // more than RUN_CAP entries in one bucket?
+      bool crowded = false;
+      for (uint32_t i = tid; i + RUN_CAP < n; i += T) crowded |= ((kB[i] - kmin) >> low) == ((kB[i + RUN_CAP] - kmin) >> low);
+      if (crowded) s_flag = 1;
+    }
+    __syncthreads();
+    if (s_flag) {  // hand the bin to the LSD kernel, which runs after this one
+      if (tid == 0) a.retry_list[atomicAdd(a.retry_count, 1u)] = bin;
+      continue;
+    }
+    uint32_t* __restrict__ out = a.vals_out + range.x;
+    for (uint32_t i = tid; i < n; i += T) {
+      const uint32_t k = kB[i], v = vB[i];
+      const uint32_t top = (k - kmin) >> low;
+      uint32_t pos = i;
+      const bool eq_prev = i > 0 && ((kB[i - 1] - kmin) >> low) == top, eq_next = i + 1 < n && ((kB[i + 1] - kmin) >> low) == top;
+      if (eq_prev || eq_next) {  // its place inside the bucket = the number of smaller (depth, index) pairs there
+        uint32_t s = i, t = i + 1, smaller = 0;
+        while (s > 0) { const uint32_t ok = kB[s - 1]; if (((ok - kmin) >> low) != top) break; s--; smaller += ok < k || (ok == k && vB[s] < v); }
+        while (t < n) { const uint32_t ok = kB[t]; if (((ok - kmin) >> low) != top) break; smaller += ok < k || (ok == k && vB[t] < v); t++; }
+        pos = s + smaller;
       }
-      block_minmax(kmn, kmx, vmn, vmx, s_mm);
-      __syncthreads();
-      sort_segment<T>(st, n, s_mm[0], s_mm[1], s_mm[2], s_mm[3], hist, s_wtot, &s_flag, a.vals_out + range.x);
-    } else {
-      SmemStore st;
-      st.kA = hist + BS_DIGITS * STR; st.vA = st.kA + CAP; st.kB = st.vA + CAP; st.vB = st.kB + CAP;
-      st.rk = reinterpret_cast<uint16_t*>(st.vB + CAP);
-      const uint2* __restrict__ src = a.entries + range.x;
-      for (uint32_t i = tid; i < n; i += T) {
-        const uint2 e = src[i];
-        st.kA[i] = e.x; st.vA[i] = e.y;
-        kmn = min(kmn, e.x); kmx = max(kmx, e.x); vmn = min(vmn, e.y); vmx = max(vmx, e.y);
-      }
-      block_minmax(kmn, kmx, vmn, vmx, s_mm);
-      __syncthreads();
-      sort_segment<T>(st, n, s_mm[0], s_mm[1], s_mm[2], s_mm[3], hist, s_wtot, &s_flag, a.vals_out + range.x);
+      out[pos] = v;
     }
   }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-template <int T, int CAP, int MIN_CTAS, bool XL>
-static cudaError_t launch_class(BinSortArgs a, int cls, const BinSortWork& w, int bins, int sm_count, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)BS_DIGITS * (T / 32 + 1) * 4 + (XL ? 0 : (size_t)CAP * 18);
+template <int T, int CAP, int MIN_CTAS>
+static cudaError_t launch_bucket_class(BinSortArgs a, int cls, const BinSortWork& w, int bins, int sm_count, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)BK_WORDS * 4 + (size_t)CAP * 8;
   static std::atomic<unsigned long long> configured{0};  // bit per device: the attribute is per (function, device)
   cudaError_t e;
   if (first_use_on_device(configured)) {
-    if ((e = cudaFuncSetAttribute(bin_sort_kernel<T, CAP, MIN_CTAS, XL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(bin_sort_kernel<T, CAP, MIN_CTAS, XL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(bucket_sort_kernel<T, CAP, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(bucket_sort_kernel<T, CAP, MIN_CTAS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return e;
   }
   a.list = w.class_list + (size_t)cls * bins;
   a.count = w.class_count + cls;
   a.next = w.class_next + cls;
   const int grid = bins < sm_count * MIN_CTAS ? bins : sm_count * MIN_CTAS;
-  bin_sort_kernel<T, CAP, MIN_CTAS, XL><<<grid, T, smem, stream>>>(a);
+  bucket_sort_kernel<T, CAP, MIN_CTAS><<<grid, T, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -279,15 +371,21 @@ cudaError_t launch_bin_sort(uint2* entries, uint2* entries_tmp, uint32_t* rank_t
   BinSortArgs a;
   a.entries = entries; a.entries_tmp = entries_tmp; a.rank_tmp = rank_tmp; a.ranges = ranges; a.vals_out = vals_out;
   a.list = nullptr; a.count = nullptr; a.next = nullptr; a.overflow = overflow;
+  // crowded bins are appended to the list of the LSD class (3), which runs last
+  a.retry_list = w.class_list + (size_t)3 * bins;
+  a.retry_count = w.class_count + 3;
   stage_mark(B200S_STAGE_BIN_SORT, stream);
   cudaError_t e;
   // longest first: the long bins of a skewed scene start while every SM is still free
-  if ((e = launch_class<1024, 0, 1, true>(a, 3, w, bins, sm_count, stream)) != cudaSuccess) return e;
-  if ((e = launch_class<1024, BIN_CAP_L, 1, false>(a, 2, w, bins, sm_count, stream)) != cudaSuccess) return e;
-  if ((e = launch_class<512, BIN_CAP_S, 2, false>(a, 1, w, bins, sm_count, stream)) != cudaSuccess) return e;
-  if ((e = launch_class<256, BIN_CAP_XS, 4, false>(a, 0, w, bins, sm_count, stream)) != cudaSuccess) return e;
+  if ((e = launch_bucket_class<1024, BIN_CAP_L, 1>(a, 2, w, bins, sm_count, stream)) != cudaSuccess) return e;
+  if ((e = launch_bucket_class<512, BIN_CAP_S, 2>(a, 1, w, bins, sm_count, stream)) != cudaSuccess) return e;
+  if ((e = launch_bucket_class<256, BIN_CAP_XS, 4>(a, 0, w, bins, sm_count, stream)) != cudaSuccess) return e;
+  a.list = w.class_list + (size_t)3 * bins;
+  a.count = w.class_count + 3;
+  a.next = w.class_next + 3;
+  lsd_sort_kernel<1024><<<bins < sm_count ? bins : sm_count, 1024, 0, stream>>>(a);
   count_launches(4);
-  return cudaSuccess;
+  return cudaGetLastError();
 }
 
 }  // namespace b200s

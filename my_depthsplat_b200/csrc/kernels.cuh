@@ -36,6 +36,8 @@ struct CompArgs {
 void stage_mark(int stage, cudaStream_t stream);
 void count_launches(int n);
 cudaError_t launch_nvls_allreduce(float* multicast, unsigned long long n_floats, int rank, int world, int sm_count, cudaStream_t stream);
+cudaError_t launch_nvls_reduce_segments(const float* multicast, float* local, const unsigned long long* off, const unsigned long long* cnt, int nseg,
+                                        int sm_count, cudaStream_t stream);
 extern std::atomic<int> g_sort_knobs[4];  // A/B switches of b200s_debug_set (debug only; never change results)
 int device_sm_count();                                       // of the current device, cached per device id
 bool first_use_on_device(std::atomic<unsigned long long>& seen);  // true once per (call site's mask, current device)
@@ -48,7 +50,8 @@ cudaError_t launch_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, ui
                         uint32_t* hist, uint64_t* lookback, uint32_t* counters, int sm_count, cudaStream_t, bool hist_ready);
 cudaError_t launch_tile_ranges(const uint64_t* keys, CountRef cnt, uint2* ranges, int bins, long long n_cap, int sm_count, cudaStream_t);
 // BINNED sort mode (preprocess.cu: count / scan / scatter; binsort.cu: per-bin segment sort)
-constexpr int BIN_CAP_XS = 2560, BIN_CAP_S = 5376, BIN_CAP_L = 11008;  // entries a bin of the class holds in shared memory
+// entries a bin of the class holds in shared memory (8 B each next to 16 KB of bucket counters; 4 / 2 / 1 CTAs per SM)
+constexpr int BIN_CAP_XS = 4960, BIN_CAP_S = 12224, BIN_CAP_L = 26976;
 constexpr int BIN_CLASSES = 4;
 struct BinSortWork {
   uint32_t* class_list;   // [BIN_CLASSES][bins] bin ids per size class

@@ -21,7 +21,8 @@ struct PreBwdArgs {
   const float* grad_rec;  // [VV,N,12]
   float* dL_dmeans2D;     // [VV,N,3] or NULL
   const uint32_t* overflow;
-  int chunk_begin, chunk_count;  // range of 256-Gaussian chunks (per scene) this launch covers
+  int chunk_begin, chunk_count;  // 256-Gaussian chunks (per scene) this launch covers: chunk_begin + r * chunk_stride + k,
+  int chunk_stride, chunk_repeat, chunks_total;  //   r < chunk_repeat, k < chunk_count, clipped to the scene
 };
 
 __device__ __forceinline__ void stage_in_bwd(float* dst, const float* __restrict__ src, int count, int k, int stride) {
@@ -80,7 +81,10 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
   constexpr int DEG = NC == 16 ? 3 : (NC == 9 ? 2 : (NC == 4 ? 1 : 0));
   constexpr int NACC = NC > 0 ? 3 * NC : 3;
   const int tid = threadIdx.x;
-  const int scene = blockIdx.x / a.chunk_count, chunk = a.chunk_begin + blockIdx.x % a.chunk_count;
+  const int per_scene = a.chunk_count * a.chunk_repeat;
+  const int scene = blockIdx.x / per_scene, lb = blockIdx.x % per_scene;
+  const int chunk = a.chunk_begin + (lb / a.chunk_count) * a.chunk_stride + lb % a.chunk_count;
+  if (chunk >= a.chunks_total) return;  // block-uniform
   const int i0 = chunk * PRE_THREADS;
   const int n = min(PRE_THREADS, a.N - i0);
   const long long g0 = (long long)scene * a.N + i0;
@@ -334,8 +338,12 @@ cudaError_t launch_preprocess_bwd(const B200sScene& sc, const B200sViews& vw, co
   const int chunks = (sc.num_gaussians + PRE_THREADS - 1) / PRE_THREADS;
   a.chunk_begin = gin.chunk_begin > 0 ? gin.chunk_begin : 0;
   a.chunk_count = gin.chunk_count > 0 ? gin.chunk_count : chunks - a.chunk_begin;
-  if (a.chunk_begin + a.chunk_count > chunks) a.chunk_count = chunks - a.chunk_begin;
-  const int blocks = a.chunk_count * sc.num_scenes;
+  a.chunk_repeat = gin.chunk_repeat > 1 ? gin.chunk_repeat : 1;
+  a.chunk_stride = a.chunk_repeat > 1 ? gin.chunk_stride : 0;
+  a.chunks_total = chunks;
+  if (a.chunk_repeat == 1 && a.chunk_begin + a.chunk_count > chunks) a.chunk_count = chunks - a.chunk_begin;
+  if (a.chunk_repeat > 1 && (a.chunk_stride < a.chunk_count || a.chunk_count <= 0)) return cudaErrorInvalidValue;
+  const int blocks = a.chunk_count * a.chunk_repeat * sc.num_scenes;
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)PRE_THREADS * (3 + a.cov_floats + a.col_stride) * sizeof(float);
   const int nc = sc.colors_precomp ? 0 : (sc.sh_degree + 1) * (sc.sh_degree + 1);

@@ -39,6 +39,15 @@ def shard_bounds(num_items: int, world_size: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def _require_views(num_views: int, world_size: int) -> None:
+    """Every rank must own at least one view: a rank without views would skip the rasterizer and with it the collectives of
+    the backward, and the other ranks would wait for it forever.  The check is on values every rank knows, so all of
+    them raise together."""
+    if num_views < world_size:
+        raise ValueError(f"{num_views} target views cannot be sharded over {world_size} ranks: every rank needs at least one "
+                         "(use a smaller process group for this call, or shard scenes instead)")
+
+
 def shard_views(t: Tensor, world_size: int, rank: int, dim: int = 1) -> Tensor:
     """Slice of a ``[B, V, ...]`` camera tensor that belongs to ``rank``."""
     a, b = shard_bounds(t.shape[dim], world_size, rank)
@@ -264,6 +273,7 @@ class ViewShardedDecoder(torch.nn.Module):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         V = extrinsics.shape[1]
+        _require_views(V, world)
         sl = [shard_views(t, world, rank) for t in (extrinsics, intrinsics, near, far)]
         fused = self.reducer is not None and self.reducer.available
         g = sync_gaussian_grads(gaussians, self.group) if (torch.is_grad_enabled() and not fused) else gaussians
@@ -273,6 +283,203 @@ class ViewShardedDecoder(torch.nn.Module):
             depth = None if out.depth is None else all_gather_views(out.depth, V, group=self.group)
             return DecoderOutput(color, depth)
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Gaussians sharded by RANGE: rank r holds (and its share of the encoder produced) the Gaussians
+# [range_bounds(N, world, r)) of every scene -- the Gaussian order is (context view, y, x), so a range is a set of context
+# views.  Forward: the ranges are all-gathered over NVLink into the full [B, N, ...] tensors every rank renders its views
+# from.  Backward: REDUCE-SCATTER -- every rank needs the summed gradient of its own range only, which halves the bytes of
+# the all-reduce, and with RangeScatterReducer the projection backward runs in pieces that each cover the j-th part of
+# EVERY rank's range, so that all ranks pull their share of piece j out of the switch (multimem.ld_reduce) on a side
+# stream while piece j + 1 is being computed.
+def range_bounds(num_gaussians: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous split in units of the kernels' 256-Gaussian chunks (the last rank's range may be short or empty)."""
+    blocks = (num_gaussians + 255) // 256
+    per = (blocks + world_size - 1) // world_size
+    return min(num_gaussians, rank * per * 256), min(num_gaussians, (rank + 1) * per * 256)
+
+
+class RangeScatterReducer:
+    """Reduce-scatter of the per-Gaussian gradients by the library's own NVLS kernel, overlapped with the projection
+    backward (see above).  The backward writes its gradients (ordinary stores) into one buffer of torch symmetric memory;
+    ``ROTATE`` buffers alternate.  The tensors it hands out have the full shape, but only this rank's Gaussian range holds
+    the cross-rank sum -- ``_GatherRanges.backward`` returns exactly that range."""
+
+    scatter = True
+    ROTATE = 3
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, pieces: int = 4):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        self.num_pieces = max(1, int(pieces))
+        self._bufs = {}
+        self._turn = 0
+        self._side = None
+        self.available = self.world > 1 and torch.cuda.is_available()
+
+    def begin(self, shapes, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        self._B, self._N = int(shapes[0][0]), int(shapes[0][1])
+        self._widths = [n // (self._B * self._N) for n in sizes]
+        offs, o = [], 0
+        for n in sizes:
+            offs.append(o)
+            o += (n + 3) // 4 * 4
+        self._offs = offs
+        key = (o, device)
+        if key not in self._bufs:
+            ring = []
+            for _ in range(self.ROTATE):
+                t = symm_mem.empty(o, dtype=torch.float32, device=device)
+                h = symm_mem.rendezvous(t, self.group)
+                if not h.multicast_ptr:
+                    self.available = False
+                    raise RuntimeError("no NVLS multicast on this fabric")
+                t.zero_()
+                ring.append((t, h))
+            self._bufs[key] = ring
+        if self._side is None:
+            self._side = torch.cuda.Stream(device)
+        self._turn = (self._turn + 1) % self.ROTATE
+        self._cur = self._bufs[key][self._turn]
+        self._piece = 0
+        buf = self._cur[0]
+        # the side stream's previous pulls (of an older buffer) are long done; order it behind the current stream once
+        self._side.wait_stream(torch.cuda.current_stream(device))
+        return [buf[a:a + n].view(s) for a, n, s in zip(offs, sizes, shapes)]
+
+    def pieces(self):
+        """(chunk_begin, chunk_count, chunk_stride, chunk_repeat) of every piece of the projection backward."""
+        blocks = (self._N + 255) // 256
+        per_rank = (blocks + self.world - 1) // self.world
+        k = self.num_pieces
+        per_piece = (per_rank + k - 1) // k
+        out = []
+        for j in range(k):
+            cn = min(per_piece, per_rank - j * per_piece)
+            if cn > 0:
+                out.append((j * per_piece, cn, per_rank, self.world))
+        self._per_rank = per_rank
+        return out
+
+    def piece_done(self, piece):
+        """The piece's kernel has been enqueued on the current stream: on the side stream, wait for it, meet the other
+        ranks, pull this rank's share of the piece."""
+        from . import _lib
+        import ctypes as C
+        buf, h = self._cur
+        dev = buf.device
+        c0, cn, _, _ = piece
+        g0 = min(self._N, (self.rank * self._per_rank + c0) * 256)
+        g1 = min(self._N, (self.rank * self._per_rank + c0 + cn) * 256)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            h.barrier(channel=2)  # every rank's piece is complete in its replica
+            segs = []
+            for b in range(self._B):
+                for off, w in zip(self._offs, self._widths):
+                    a0, a1 = off + (b * self._N + g0) * w, off + (b * self._N + g1) * w
+                    a1 = (a1 + 3) // 4 * 4  # the ragged end of a tensor runs into its alignment padding
+                    if a1 > a0:
+                        segs.append((a0, a1 - a0))
+            L = _lib.load()
+            for i in range(0, len(segs), 16):
+                part = segs[i:i + 16]
+                so = (C.c_ulonglong * len(part))(*[p[0] for p in part])
+                sn = (C.c_ulonglong * len(part))(*[p[1] for p in part])
+                _lib.check(L.b200s_nvls_reduce_segments(h.multicast_ptr, buf.data_ptr(), so, sn, len(part), self._side.cuda_stream),
+                           "b200s_nvls_reduce_segments")
+
+    def end(self):
+        buf, _ = self._cur
+        torch.cuda.current_stream(buf.device).wait_stream(self._side)
+
+
+class _GatherRanges(torch.autograd.Function):
+    """forward: the ranks' Gaussian ranges all-gathered into the full tensors; backward: this rank's range of the gradient
+    of the full tensors, summed over the ranks (by the rasterizer's RangeScatterReducer when ``kernel_reduced``, else by a
+    reduce-scatter / all-reduce here)."""
+
+    @staticmethod
+    def forward(ctx, group, num_gaussians, kernel_reduced, *local):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        N = int(num_gaussians)
+        bounds = [range_bounds(N, world, r) for r in range(world)]
+        ctx.group, ctx.bounds, ctx.rank, ctx.kernel_reduced = group, bounds, rank, kernel_reduced
+        lo, hi = bounds[rank]
+        even = all(b - a == hi - lo for a, b in bounds)
+        outs = []
+        for t in local:
+            B = t.shape[0]
+            if t.shape[1] != hi - lo:
+                raise ValueError(f"rank {rank} must pass its Gaussian range [{lo}, {hi}) of every tensor, got {tuple(t.shape)}")
+            full = t.new_empty((B, N) + tuple(t.shape[2:]))
+            if even and B == 1:
+                dist.all_gather_into_tensor(full.view(-1), t.contiguous().view(-1), group=group)
+            else:
+                nmax = max(b - a for a, b in bounds)
+                pad = t.new_zeros((B, nmax) + tuple(t.shape[2:]))
+                pad[:, :hi - lo] = t
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad, group=group)
+                for p_, (a, b) in zip(parts, bounds):
+                    full[:, a:b] = p_[:, :b - a]
+            outs.append(full)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lo, hi = ctx.bounds[ctx.rank]
+        if ctx.kernel_reduced:
+            return (None, None, None, *[g[:, lo:hi] for g in grads])
+        world = len(ctx.bounds)
+        even = all(b - a == hi - lo for a, b in ctx.bounds)
+        out = []
+        for g in grads:
+            g = g.contiguous()
+            if even and g.shape[0] == 1 and g.is_cuda:
+                mine = g.new_empty((1, hi - lo) + tuple(g.shape[2:]))
+                dist.reduce_scatter_tensor(mine.view(-1), g.view(-1), op=dist.ReduceOp.SUM, group=ctx.group)
+                out.append(mine)
+            else:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+                out.append(g[:, lo:hi])
+        return (None, None, None, *out)
+
+
+class RangeShardedDecoder(torch.nn.Module):
+    """Every rank passes ITS range of the Gaussians (``range_bounds``) and the cameras of ALL target views; it renders its
+    contiguous slice of the views from the all-gathered Gaussians and gets back the gradient of its own range, summed
+    over all ranks' views.  ``num_gaussians`` is N, the Gaussians per scene over all ranks."""
+
+    def __init__(self, decoder: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, pieces: int = 4, kernel_reduce: bool = True):
+        super().__init__()
+        self.decoder = decoder
+        self.group = group
+        self.reducer = None
+        if kernel_reduce and dist.is_initialized() and dist.get_world_size(group) > 1 and torch.cuda.is_available() and hasattr(decoder, "grad_reducer"):
+            self.reducer = RangeScatterReducer(group, pieces)
+
+    def forward(self, local: Gaussians, num_gaussians: int, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                image_shape: tuple[int, int], depth_mode=None) -> DecoderOutput:
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        if world == 1:
+            return self.decoder.forward(local, extrinsics, intrinsics, near, far, image_shape, depth_mode=depth_mode)
+        _require_views(extrinsics.shape[1], world)
+        # the NVLS kernel moves 16-byte vectors: every scene's tensors must start on one
+        aligned = local.means.shape[0] == 1 or num_gaussians % 4 == 0
+        by_kernel = self.reducer is not None and self.reducer.available and torch.is_grad_enabled() and aligned
+        if hasattr(self.decoder, "grad_reducer"):
+            self.decoder.grad_reducer = self.reducer if by_kernel else None
+        m, c, h, o = _GatherRanges.apply(self.group, num_gaussians, by_kernel, local.means, local.covariances, local.harmonics, local.opacities)
+        sl = [shard_views(t, world, rank) for t in (extrinsics, intrinsics, near, far)]
+        return self.decoder.forward(Gaussians(m, c, h, o), *sl, image_shape, depth_mode=depth_mode)
 
 
 def render_sharded(render_fn: Callable[..., Sequence[Tensor]], gaussians: Gaussians, cameras: Sequence[Tensor], *args,

@@ -372,7 +372,19 @@ class _Rasterize(torch.autograd.Function):
             _lib.check(L.b200s_backward(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(), C.byref(out),
                                         C.byref(gout), C.byref(gin), stream), "b200s_backward")
 
-        if reducer is not None and getattr(reducer, "in_place", False):
+        if reducer is not None and getattr(reducer, "scatter", False):
+            # reduce-scatter by Gaussian range: outputs are views of a symmetric-memory buffer; the projection backward runs
+            # in pieces that each cover a part of EVERY rank's range, and the reducer pulls this rank's share of a finished
+            # piece out of the NVSwitch on a side stream while the next piece is computed
+            d_means, d_covs, d_colors, d_op = reducer.begin([means.shape, covs.shape, colors.shape, opacities.shape], dev)
+            mk = lambda stages, pc: _lib.GradIn(_ptr(d_means), _ptr(d_covs), _ptr(d_colors) if use_sh else None,
+                                                None if use_sh else _ptr(d_colors), _ptr(d_op), _ptr(d_m2d), 0, stages, *pc)
+            call(mk(1, (0, 0, 0, 0)))
+            for pc in reducer.pieces():
+                call(mk(2, pc))
+                reducer.piece_done(pc)
+            reducer.end()
+        elif reducer is not None and getattr(reducer, "in_place", False):
             # outputs are views of a symmetric-memory buffer; the reducer sums it over the ranks in place afterwards
             d_means, d_covs, d_colors, d_op = reducer.begin([means.shape, covs.shape, colors.shape, opacities.shape], dev)
             call(_lib.GradIn(_ptr(d_means), _ptr(d_covs), _ptr(d_colors) if use_sh else None, None if use_sh else _ptr(d_colors),

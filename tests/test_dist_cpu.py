@@ -66,7 +66,24 @@ def _worker(rank, world, port, result_dir):
             t.fill_(float((rank + 1) * (i + 1)))
         torch.autograd.backward(D._SyncGrads.apply(None, *xs), grad_tensors=list(carved))
         flat_sums = [float(x.grad.min()) for x in xs] + [float(x.grad.max()) for x in xs]
-        torch.save({"color": full.color, "depth": full.depth, "flat_sums": flat_sums, "clip_color": clip.color, "clip_depth": clip.depth, "grads": [g.means.grad, g.covariances.grad, g.harmonics.grad, g.opacities.grad]},
+        # --- Gaussians sharded by range: all-gather in the forward, this rank's range of the summed gradients back
+        from my_depthsplat_b200.types import Gaussians
+        N = scene.gaussians.means.shape[1]
+        glo, ghi = D.range_bounds(N, world, rank)
+        mine = Gaussians(*(t[:, glo:ghi].detach().clone().requires_grad_() for t in
+                           (scene.gaussians.means, scene.gaussians.covariances, scene.gaussians.harmonics, scene.gaussians.opacities)))
+        rdec = D.RangeShardedDecoder(OracleDecoder())
+        rout = rdec.forward(mine, N, scene.extrinsics, scene.intrinsics, scene.near, scene.far, scene.image_shape, depth_mode="depth")
+        assert torch.equal(rout.color, out.color.detach())
+        ((rout.color * scene.grad_color[:, lo:hi]).sum() + (rout.depth * scene.grad_depth[:, lo:hi]).sum()).backward()
+        range_grads = [mine.means.grad, mine.covariances.grad, mine.harmonics.grad, mine.opacities.grad]
+        # --- fewer views than ranks: every rank raises the same error instead of one of them hanging the others
+        try:
+            dec.forward(g, scene.extrinsics[:, :1], scene.intrinsics[:, :1], scene.near[:, :1], scene.far[:, :1], scene.image_shape)
+            too_few = "no error"
+        except ValueError as e:
+            too_few = str(e)
+        torch.save({"range": (glo, ghi), "range_grads": range_grads, "too_few": too_few, "color": full.color, "depth": full.depth, "flat_sums": flat_sums, "clip_color": clip.color, "clip_depth": clip.depth, "grads": [g.means.grad, g.covariances.grad, g.harmonics.grad, g.opacities.grad]},
                    Path(result_dir) / f"rank{rank}.pt")
     finally:
         dist.destroy_process_group()
@@ -105,6 +122,13 @@ def test_view_sharded_decoder_two_ranks(tmp_path):
             torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-6 * float(ref.abs().max()))  # sum order differs
     for a, b in zip(res[0]["grads"], res[1]["grads"]):
         assert torch.equal(a, b)  # every rank holds the same reduced gradients
+    # range sharding: the ranges tile the Gaussians, every rank holds the summed gradient of its own range
+    assert res[0]["range"][0] == 0 and res[0]["range"][1] == res[1]["range"][0] and res[1]["range"][1] == g.means.shape[1]
+    for r in res:
+        glo, ghi = r["range"]
+        assert "cannot be sharded" in r["too_few"]
+        for got, ref in zip(r["range_grads"], (g.means.grad, g.covariances.grad, g.harmonics.grad, g.opacities.grad)):
+            torch.testing.assert_close(got, ref[:, glo:ghi], rtol=1e-4, atol=1e-6 * float(ref.abs().max()))
 
 
 def test_flat_span_recognises_only_gapless_tilings():

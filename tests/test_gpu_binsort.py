@@ -1,7 +1,8 @@
 """The BINNED sort mode's per-bin segment sort (csrc/binsort.cu) through b200s_segment_sort, against numpy: every bin's
 values in ascending (key, value) order -- what a stable sort of pairs emitted in value order produces -- whatever the
-arrival order inside the bin.  Covers all four size classes (shared-memory XS / S / L, global-memory XL), empty bins,
-duplicate keys (short runs: rank fix-up; long runs: the index-pass fallback) and narrow / wide key ranges."""
+arrival order inside the bin.  Covers the three shared-memory size classes of the bucket path, the global-memory LSD path
+(bins longer than 26 976 entries, and bins handed over because a bucket was crowded), empty bins, duplicate keys (short
+runs: rank inside the bucket; long runs: the LSD path's index passes) and narrow / wide key ranges."""
 import numpy as np
 import pytest
 import torch
@@ -36,7 +37,7 @@ def _expect(counts, keys, vals):
 
 
 CASES = {
-    "mixed_classes": dict(counts=[0, 1, 31, 33, 700, 2560, 2561, 5376, 5377, 0, 11008, 11009, 30000, 5], keybits=32, dup=0.0),
+    "mixed_classes": dict(counts=[0, 1, 31, 33, 65, 700, 4960, 4961, 12224, 12225, 0, 26976, 26977, 70000, 5], keybits=32, dup=0.0),
     "narrow_range_ties": dict(counts=[4000, 9000, 100, 20000], keybits=9, dup=0.0),       # 512 distinct keys: runs of ~10-40
     "float_depths": dict(counts=[4400] * 40 + [8300] * 8, keybits=None, dup=0.001),
     "all_equal_keys": dict(counts=[3000, 7000, 15000, 64], keybits=0, dup=0.0),          # one run per bin: index-pass fallback

@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from my_depthsplat_b200.decoder_splatting_cuda import DecoderSplattingCUDACfg, get_decoder  # noqa: E402
-from my_depthsplat_b200.dist import ViewShardedDecoder, shard_bounds  # noqa: E402
+from my_depthsplat_b200.dist import RangeShardedDecoder, ViewShardedDecoder, range_bounds, shard_bounds  # noqa: E402
 from my_depthsplat_b200.scenes import make_scene  # noqa: E402
 from my_depthsplat_b200.types import Gaussians  # noqa: E402
 
@@ -45,8 +45,35 @@ ovl_dec = ViewShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting
 ovl = grads(ovl_dec, (lo, hi))
 nvls_dec = ViewShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), nvls_reduce=True)
 nvls = [[t.clone() for t in grads(nvls_dec, (lo, hi))] for _ in range(4)]  # four calls: the buffer ring wraps around
+# (e) Gaussians sharded by range: all-gather in the forward, reduce-scatter in the backward -- by the library's NVLS kernel in
+# pieces under the projection backward, and by NCCL
+N = sc.gaussians.means.shape[1]
+glo, ghi = range_bounds(N, world, rank)
+
+
+def range_grads(dec):
+    g = sc.gaussians
+    leaves = [t[:, glo:ghi].detach().clone().requires_grad_() for t in (g.means, g.covariances, g.harmonics, g.opacities)]
+    out = dec.forward(Gaussians(*leaves), N, sc.extrinsics, sc.intrinsics, sc.near, sc.far, (H, W), depth_mode="depth")
+    loss = (out.color * sc.grad_color[:, lo:hi]).sum() + (out.depth * sc.grad_depth[:, lo:hi]).sum()
+    return [t.clone() for t in torch.autograd.grad(loss, leaves)]
+
+
+rk_dec = RangeShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), pieces=3)
+rk = [range_grads(rk_dec) for _ in range(4)]   # four calls: the symmetric buffers rotate
+rn = range_grads(RangeShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), kernel_reduce=False))
 torch.cuda.synchronize()
 ok = True
+for k, nm in enumerate(("means", "covariances", "harmonics", "opacities")):
+    ref = single[k][:, glo:ghi]
+    scale = float(single[k].abs().max())
+    if ref.numel() == 0:
+        continue
+    e_k = max(float((rk[j][k] - ref).abs().max()) / scale for j in range(4))
+    e_n = float((rn[k] - ref).abs().max()) / scale
+    print(f"rank {rank} {nm:12s} range [{glo}, {ghi}): |NVLS reduce-scatter - single| {e_k:.2e} (4 calls)  |NCCL reduce-scatter - single| {e_n:.2e}", flush=True)
+    ok &= e_k < 2e-4 and e_n < 2e-4
+print(f"rank {rank} range reducer active: {rk_dec.reducer is not None and rk_dec.reducer.available}", flush=True)
 for nm, s, a, b, c, d in zip(("means", "covariances", "harmonics", "opacities"), single, nccl, fused, fused2, ovl):
     scale = float(s.abs().max())
     e_n, e_f, e_f2, e_o = (float((x - s).abs().max()) / scale for x in (a, b, c, d))
