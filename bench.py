@@ -226,23 +226,37 @@ def run_ours(args):
     B_local = host["means"].shape[0]
     host = {k: v.pin_memory() for k, v in host.items()}
     devt = {k: v.to(dev) for k, v in host.items()}
+    # End-to-end leg at N > 1: every rank's HOST holds only its contiguous RANGE of the Gaussians (what its share of the encoder
+    # produced): 1/N of the bytes cross PCIe per rank, the ranks all-gather the ranges over NVLink, and every rank reads back its
+    # frames and the summed gradient of its own range (reduce-scatter).  --e2e-replicated keeps the value leg's layout instead.
+    e2e_ranges = world > 1 and not by_scene and not by_range and not args.e2e_replicated
+    if e2e_ranges:
+        gs_e = slice(*range_bounds(N, world, rank))
+        host_e = dict(host)
+        for k in ("means", "covariances", "harmonics", "opacities"):
+            host_e[k] = getattr(g_, k)[bs, gs_e].contiguous().pin_memory()
+    else:
+        host_e = host
     dataset_cfg = type("DatasetCfg", (), {"background_color": [0.0, 0.0, 0.0]})()
     decoder = get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), dataset_cfg).to(dev)
     # view sharding + ONE NCCL all-reduce of the flattened per-Gaussian gradients in the backward (identity at N=1)
     full_dev = {k: getattr(g_, k)[bs].to(dev) for k in ("means", "covariances", "harmonics", "opacities")} if by_range else devt
-    ranged = RangeShardedDecoder(decoder, pieces=args.pieces, kernel_reduce=not args.nccl_scatter) if by_range else None
+    ranged = RangeShardedDecoder(decoder, pieces=args.pieces, kernel_reduce=not args.nccl_scatter) if (by_range or e2e_ranges) else None
+    scatter = world > 1 and args.grads == "scatter" and not (args.fused_reduce or args.overlap_reduce or args.nvls_reduce)
     sharded = decoder if (by_scene or by_range) else ViewShardedDecoder(
         decoder, fused_reduce=(world > 1 and args.fused_reduce), overlap_reduce=(world > 1 and args.overlap_reduce),
-        nvls_reduce=(world > 1 and args.nvls_reduce))
+        nvls_reduce=(world > 1 and args.nvls_reduce), scatter_grads=scatter, pieces=args.pieces)
     if getattr(sharded, "reducer", None) is not None and hasattr(sharded.reducer, "chunks") and os.environ.get("B200S_REDUCE_CHUNKS"):
         sharded.reducer.chunks = int(os.environ["B200S_REDUCE_CHUNKS"])
     gnames = ("means", "covariances", "harmonics", "opacities")
 
-    def step(t):
+    def step(t, ranges=by_range):
         leaves = [t[k].detach().requires_grad_() for k in gnames]
-        if by_range:
+        if ranges:
             out = ranged.forward(Gaussians(*leaves), N, t["extrinsics"], t["intrinsics"], t["near"], t["far"], (H, W), depth_mode=None)
         else:
+            if hasattr(decoder, "grad_reducer") and not by_scene:
+                decoder.grad_reducer = getattr(sharded, "reducer", None)
             out = sharded.forward(Gaussians(*leaves), t["extrinsics"], t["intrinsics"], t["near"], t["far"], (H, W), depth_mode=None)
         grads = torch.autograd.grad(out.color, leaves, t["grad_color"])
         return out.color, grads
@@ -254,7 +268,7 @@ def run_ours(args):
     # buffered, so the H2D of step i+1 and the D2H of step i-1 overlap the kernels of step i (PCIe is full
     # duplex); every byte of every step still crosses the bus inside the timed region.
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in host_e.items()} for _ in range(2)]
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
     ev_done = torch.cuda.Event()
@@ -264,7 +278,7 @@ def run_ours(args):
     def enqueue_h2d(slot):
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_free[slot])  # the step that last used this slot has finished reading it
-            for k, v in host.items():
+            for k, v in host_e.items():
                 dev_in[slot][k].copy_(v, non_blocking=True)
             ev_in[slot].record(s_in)
 
@@ -277,7 +291,7 @@ def run_ours(args):
         cur.wait_event(ev_in[slot])
         enqueue_h2d(slot ^ 1)           # next step's inputs start travelling now
         e2e_state["pending"] = i + 1
-        color, grads = step(dev_in[slot])
+        color, grads = step(dev_in[slot], ranges=(by_range or e2e_ranges))
         ev_free[slot].record(cur)
         # detach: copy_() from a tensor with history would chain every step's autograd graph onto host_out
         outs = [color.detach()] + [g.detach() for g in (grads if isinstance(grads, (tuple, list)) else [grads])]
@@ -354,7 +368,7 @@ def run_ours(args):
     pcie = {"h2d_gbs": round(copy_gbs(devt["harmonics"], host["harmonics"]), 2),
             "d2h_gbs": round(copy_gbs(host_out[1] if 1 in host_out and host_out[1].shape == devt["means"].shape else host["means"], devt["means"]), 2)}
     ms_step_e = ms_e / args.steps
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = sum(v.numel() * v.element_size() for v in host_e.values())
     d2h = sum(v.numel() * v.element_size() for v in host_out.values())
     e2e_value = pix_step / (ms_step_e * 1e-3) / 1e6
 
@@ -482,10 +496,12 @@ def run_ours(args):
                        "parallelism": (f"scene-sharded x{world}: {B_local} scene(s) per GPU, no collective on the rendering path") if by_scene else
                        (f"view-sharded x{world}, Gaussians sharded by range ({N // world} per rank): NCCL all-gather over NVLink in the forward, "
                         + ("NCCL reduce-scatter" if args.nccl_scatter else f"reduce-scatter by the library's NVLS kernel (multimem.ld_reduce) in {args.pieces} pieces under the projection backward")
-                        + " of the per-Gaussian gradients in the backward") if by_range else f"view-sharded x{world}, Gaussians replicated" + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
-                                        else (", NCCL all-reduce of per-Gaussian grads" + (" in 2 chunks overlapped with the projection backward" if args.overlap_reduce else ""))) if world > 1 else "")},
+                        + " of the per-Gaussian gradients in the backward") if by_range else f"view-sharded x{world}, Gaussians replicated" + (f", per-Gaussian gradients reduce-scattered by Gaussian range (library NVLS kernel, {args.pieces} pieces under the projection backward)" if scatter else "") + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
+                                        else ("" if scatter else ", NCCL all-reduce of per-Gaussian grads" + (" in 2 chunks overlapped with the projection backward" if args.overlap_reduce else ""))) if world > 1 else "")},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_step_e, 4), "pinned_copy_bandwidth": pcie, "allocator_events": alloc_events,
+                    "layout": ("every rank's host holds its 1/N range of the Gaussians; NCCL all-gather over NVLink, reduce-scatter of the gradients, "
+                               "each rank reads back its frames and its range's gradients") if e2e_ranges else "the value leg's layout",
                     "note": "3-stream pipeline: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i"},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -512,6 +528,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2T")
     ap.add_argument("--views", type=int, default=0, help="target views per GPU (default: the config's)")
+    ap.add_argument("--e2e-replicated", action="store_true", help="N>1: the e2e leg copies the full replicated Gaussians per rank (round-1 layout)")
+    ap.add_argument("--grads", default="scatter", choices=["allreduce", "scatter"],
+                    help="N>1, --shard views: all-reduce of the per-Gaussian gradients (every rank gets all of them), or reduce-scatter "
+                         "(every rank gets the summed gradient of ITS Gaussian range, zeros elsewhere; pulled out of the NVSwitch in "
+                         "pieces under the projection backward)")
     ap.add_argument("--pieces", type=int, default=4, help="--shard ranges: pieces of the projection backward (one reduce-scatter pull each)")
     ap.add_argument("--nccl-scatter", action="store_true", help="--shard ranges: NCCL reduce_scatter after the backward instead of the NVLS kernel")
     ap.add_argument("--shard", default="views", choices=["views", "scenes", "ranges"],

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 8
+#define B200S_ABI_VERSION 9
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -159,11 +159,23 @@ typedef struct B200sOut {
                         Stage A stores {u64 num_pairs, u32 overflow flag, u32 nonzero marker (BINNED: 0x80000000 |
                         max_bin_len)} there directly from the kernel, so the host can read the pair count after an
                         event wait (or lazily, much later) without occupying a copy engine. */
+  /* Optional loss-side fusion: the reference computes weight * mean((color - target)^2) (or the mean
+   * absolute error) over the decoder's colour in PyTorch (src/loss/loss_mse.py:33-44) and the PSNR of the clipped images
+   * (src/evaluation/metrics.py:11-19), and autograd turns the loss into dL/dcolor = 2 weight (color - target) / n in further
+   * passes over the images.  With mse_target set, the compositing epilogue does all of it while the pixel is in registers. */
+  const float* mse_target; /* [VV,3,H,W] ground-truth images, or NULL */
+  float* mse_grad;         /* [VV,3,H,W] dL/dcolor of the loss, ready to be passed as B200sGradOut.dL_dcolor */
+  float* mse_partials;     /* [VV, tiles, 2] per (view, tile): sum of squared (l1: absolute) error; sum of squared error of the
+                              images clipped to [0, 1] (PSNR).  Fixed-order sums: the loss is reproducible */
+  float mse_scale;         /* weight / n, n = number of colour values the mean runs over */
+  int32_t mse_l1;          /* != 0: mean absolute error (l1_loss=True) */
 } B200sOut;
 
 typedef struct B200sGradOut { /* upstream gradients */
   const float* dL_dcolor; /* [VV,3,H,W] */
   const float* dL_ddepth; /* [VV,H,W] or NULL */
+  const float* dL_dcolor_scale; /* optional DEVICE scalar every dL_dcolor value is multiplied by on load -- the upstream gradient of
+                                   a loss whose dL/dcolor the forward epilogue produced (B200sOut.mse_grad): no scaling pass */
 } B200sGradOut;
 
 typedef struct B200sGradIn { /* all fp32, OVERWRITTEN (summed over the views of each scene) */

@@ -10,7 +10,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200splat.so"
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 B200S_OK, B200S_EBADARG, B200S_ECUDA = 0, 1, 3
 COV_3X3, COV_UPPER6 = 0, 1
@@ -68,11 +68,12 @@ class Status(C.Structure):
 
 
 class Out(C.Structure):
-    _fields_ = [("color", _f32p), ("depth", _f32p), ("radii", C.c_void_p), ("count_work", C.c_int32), ("status_host", C.c_void_p)]
+    _fields_ = [("color", _f32p), ("depth", _f32p), ("radii", C.c_void_p), ("count_work", C.c_int32), ("status_host", C.c_void_p),
+                ("mse_target", _f32p), ("mse_grad", _f32p), ("mse_partials", _f32p), ("mse_scale", C.c_float), ("mse_l1", C.c_int32)]
 
 
 class GradOut(C.Structure):
-    _fields_ = [("dL_dcolor", _f32p), ("dL_ddepth", _f32p)]
+    _fields_ = [("dL_dcolor", _f32p), ("dL_ddepth", _f32p), ("dL_dcolor_scale", _f32p)]
 
 
 class GradIn(C.Structure):

@@ -247,6 +247,11 @@ int b200s_forward_render(const B200sScene* sc, const B200sViews* vw, const B200s
   a.final_T = reinterpret_cast<float*>(saved + pl->off_final_T);
   a.n_contrib = reinterpret_cast<uint32_t*>(saved + pl->off_n_contrib);
   a.status = st;
+  if (out->mse_target) {
+    if (!out->mse_grad || !out->mse_partials) return B200S_EBADARG;
+    a.mse_target = out->mse_target; a.mse_grad = out->mse_grad; a.mse_partials = out->mse_partials;
+    a.mse_scale = out->mse_scale; a.mse_l1 = out->mse_l1;
+  }
   e = launch_composite_fwd(a, pl->tiles, vw->num_views, vw->depth_mode != B200S_DEPTH_NONE, out->count_work != 0, stream);
   stage_mark(B200S_STAGE_END, stream);
   return e == cudaSuccess ? B200S_OK : fail(e);
@@ -279,7 +284,7 @@ int b200s_backward(const B200sScene* sc, const B200sViews* vw, const B200sPlan* 
   a.bg = vw->background; a.overflow = &st->overflow;
   a.final_T = const_cast<float*>(reinterpret_cast<const float*>(saved + pl->off_final_T));
   a.n_contrib = const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(saved + pl->off_n_contrib));
-  a.dL_dcolor = gout->dL_dcolor; a.dL_ddepth = gout->dL_ddepth; a.grad_rec = grad_rec;
+  a.dL_dcolor = gout->dL_dcolor; a.dL_ddepth = gout->dL_ddepth; a.dpix_scale = gout->dL_dcolor_scale; a.grad_rec = grad_rec;
   e = launch_composite_bwd(a, pl->tiles, vw->num_views, vw->depth_mode != B200S_DEPTH_NONE, stream);
   if (e != cudaSuccess) return fail(e);
   }

@@ -72,9 +72,10 @@ struct __align__(16) HitSlot {
 };
 
 // -------------------------------------------------------------------------------------------------
-template <bool DEPTH, bool COUNT>
+template <bool DEPTH, bool COUNT, bool LOSS>
 __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs a) {
   __shared__ HitSlot s_slot[WARPS][32];
+  __shared__ float s_loss[LOSS ? WARPS : 1][2];
   if (*a.overflow) return;
   const int tile = blockIdx.x, view = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs 
   HitSlot* const slots = s_slot[warp];
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+  float loss_sum = 0.f, psnr_sum = 0.f;
   uint32_t last = 0, nblend = 0;
   bool done = !g.inside;
 
@@ -146,12 +148,37 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs 
     const size_t pid = (size_t)g.py * a.W + g.px;
     const float* bg = a.bg + view * 3;
     float* col = a.color + (size_t)view * 3 * HW;
-    col[pid] = __fmaf_rn(T, bg[0], C0);
-    col[HW + pid] = __fmaf_rn(T, bg[1], C1);
-    col[2 * HW + pid] = __fmaf_rn(T, bg[2], C2);
+    const float c[3] = {__fmaf_rn(T, bg[0], C0), __fmaf_rn(T, bg[1], C1), __fmaf_rn(T, bg[2], C2)};
+    col[pid] = c[0];
+    col[HW + pid] = c[1];
+    col[2 * HW + pid] = c[2];
     if (DEPTH) a.depth[(size_t)view * HW + pid] = D;
     a.final_T[(size_t)view * HW + pid] = T;
     a.n_contrib[(size_t)view * HW + pid] = last;
+    if (LOSS) {  // the loss and its gradient while the pixel is in registers (loss_mse.py:33-44, metrics.py:11-19)
+      const float* gt = a.mse_target + (size_t)view * 3 * HW + pid;
+      float* gr = a.mse_grad + (size_t)view * 3 * HW + pid;
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        const float t = __ldg(gt + ch * HW), d = c[ch] - t;
+        gr[ch * HW] = a.mse_l1 ? (d > 0.f ? a.mse_scale : (d < 0.f ? -a.mse_scale : 0.f)) : 2.0f * a.mse_scale * d;
+        loss_sum += a.mse_l1 ? fabsf(d) : d * d;
+        const float dc = fminf(fmaxf(c[ch], 0.f), 1.f) - fminf(fmaxf(t, 0.f), 1.f);
+        psnr_sum += dc * dc;
+      }
+    }
+  }
+  if (LOSS) {  // fixed-order sums: lanes, then the eight warps, one (view, tile) slot each -- no atomics
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { loss_sum += __shfl_xor_sync(0xffffffffu, loss_sum, d); psnr_sum += __shfl_xor_sync(0xffffffffu, psnr_sum, d); }
+    if (lane == 0) { s_loss[warp][0] = loss_sum; s_loss[warp][1] = psnr_sum; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) t += s_loss[w][threadIdx.x];
+      a.mse_partials[((size_t)view * gridDim.x + tile) * 2 + threadIdx.x] = t;
+    }
   }
   if (COUNT) {
     unsigned long long t = g.inside ? last : 0, b = nblend;
@@ -272,9 +299,10 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel
 #pragma unroll
   for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) s.dpix[ch] = 0.f;
   if (g.inside) {
+    const float cs = a.dpix_scale ? __ldg(a.dpix_scale) : 1.0f;
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
-      s.dpix[ch] = a.dL_dcolor[((size_t)view * 3 + ch) * HW + pid];
+      s.dpix[ch] = a.dL_dcolor[((size_t)view * 3 + ch) * HW + pid] * cs;
       bg_dot += a.bg[view * 3 + ch] * s.dpix[ch];
     }
     if (DEPTH) s.dpix[3] = a.dL_ddepth[(size_t)view * HW + pid];
@@ -402,8 +430,11 @@ cudaError_t launch_composite_fwd(const CompArgs& a, int tiles, int views, bool d
   dim3 grid(tiles, views);
   stage_mark(B200S_STAGE_COMP_FWD, stream);
   count_launches(1);
-  if (depth) { if (count) composite_fwd_kernel<true, true><<<grid, TILE_PIX, 0, stream>>>(a); else composite_fwd_kernel<true, false><<<grid, TILE_PIX, 0, stream>>>(a); }
-  else { if (count) composite_fwd_kernel<false, true><<<grid, TILE_PIX, 0, stream>>>(a); else composite_fwd_kernel<false, false><<<grid, TILE_PIX, 0, stream>>>(a); }
+  const bool loss = a.mse_target != nullptr;
+#define FWD(D_, C_, L_) composite_fwd_kernel<D_, C_, L_><<<grid, TILE_PIX, 0, stream>>>(a)
+  if (depth) { if (count) { if (loss) FWD(true, true, true); else FWD(true, true, false); } else { if (loss) FWD(true, false, true); else FWD(true, false, false); } }
+  else { if (count) { if (loss) FWD(false, true, true); else FWD(false, true, false); } else { if (loss) FWD(false, false, true); else FWD(false, false, false); } }
+#undef FWD
   return cudaGetLastError();
 }
 cudaError_t launch_composite_bwd(const CompArgs& a, int tiles, int views, bool depth, cudaStream_t stream) {

@@ -26,9 +26,16 @@ struct CompArgs {
   float* final_T;          // [VV,H,W]
   uint32_t* n_contrib;     // [VV,H,W]
   B200sStatus* status;
+  // loss-side fusion (forward epilogue)
+  const float* mse_target; // [VV,3,H,W] or NULL
+  float* mse_grad;         // [VV,3,H,W]
+  float* mse_partials;     // [VV,tiles,2]
+  float mse_scale;
+  int mse_l1;
   // backward
   const float* dL_dcolor;  // [VV,3,H,W]
   const float* dL_ddepth;  // [VV,H,W] or NULL
+  const float* dpix_scale; // device scalar on dL_dcolor, or NULL
   float* grad_rec;         // [VV,N,12]
 };
 
@@ -63,7 +70,7 @@ cudaError_t launch_bin_sort(uint2* entries, uint2* entries_tmp, uint32_t* rank_t
 // scan of per-bin counts -> ranges, cursors, size-class lists, pair total (+ overflow flag, host status word)
 cudaError_t launch_bin_scan(const uint32_t* bin_count, int bins, uint2* ranges, uint32_t* cursor, const BinSortWork& w,
                             B200sStatus* status, unsigned long long pair_capacity, unsigned long long* status_host, cudaStream_t);
-cudaError_t launch_composite_fwd(const CompArgs&, int tiles, int views, bool depth, bool count, cudaStream_t);
+cudaError_t launch_composite_fwd(const CompArgs&, int tiles, int views, bool depth, bool count, cudaStream_t);  // loss fusion iff mse_target
 cudaError_t launch_composite_bwd(const CompArgs&, int tiles, int views, bool depth, cudaStream_t);
 cudaError_t launch_preprocess_bwd(const B200sScene&, const B200sViews&, const B200sPlan&, const char* saved, char* scratch,
                                   const B200sGradIn&, cudaStream_t);

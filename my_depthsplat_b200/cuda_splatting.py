@@ -179,16 +179,24 @@ def render_views(
     want_radii: bool = False,
     count_work: bool = False,
     grad_reducer=None,
+    mse: Optional[dict] = None,
 ):
     """All V views of all B scenes in one rasterizer call.  Returns (color [B,V,3,H,W],
-    depth [B,V,H,W] | None) (+ radii [B,V,N] when want_radii)."""
+    depth [B,V,H,W] | None) (+ radii [B,V,N] when want_radii).
+
+    ``mse`` (loss-side fusion) = dict(target=[B,V,3,H,W], weight=float, l1=bool[, count=int]): the
+    compositing epilogue also computes weight * mean((color - target)^2) (src/loss/loss_mse.py:33-44), its dL/dcolor and the
+    clipped squared error of compute_psnr (src/evaluation/metrics.py:11-19); the dict comes back with "loss" (differentiable
+    scalar; its backward feeds the rasterizer's backward directly) and "sse_clipped" [B,V]."""
     B, V = extrinsics.shape[:2]
     h, w = image_shape
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    if mse is not None and "count" not in mse:
+        mse["count"] = B * V * 3 * h * w
     try:
         return _render_views_once(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
                                   gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh,
-                                  depth_mode, want_radii, count_work, grad_reducer)
+                                  depth_mode, want_radii, count_work, grad_reducer, mse)
     except PairLimitExceeded:
         if V == 1:
             raise
@@ -196,9 +204,14 @@ def render_views(
     # concatenate -- each half is its own autograd node, gradients add up as usual
     half = V // 2
     bgs = (background_color, background_color) if background_color.dim() == 1 else (background_color[:, :half], background_color[:, half:])
+    sls = (slice(0, half), slice(half, V))
+    sub = [None if mse is None else dict(target=mse["target"][:, sl], weight=mse["weight"], l1=mse.get("l1", False), count=mse["count"]) for sl in sls]
     parts = [render_views(extrinsics[:, sl], intrinsics[:, sl], near[:, sl], far[:, sl], image_shape, bg, gaussian_means,
                           gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode,
-                          want_radii, count_work, grad_reducer) for sl, bg in zip((slice(0, half), slice(half, V)), bgs)]
+                          want_radii, count_work, grad_reducer, m) for sl, bg, m in zip(sls, bgs, sub)]
+    if mse is not None:  # both halves divide by the count of the whole call: the loss is their sum
+        mse["loss"] = sub[0]["loss"] + sub[1]["loss"]
+        mse["sse_clipped"] = torch.cat([sub[0]["sse_clipped"], sub[1]["sse_clipped"]], dim=1)
     out = [torch.cat([p[0] for p in parts], dim=1),
            None if parts[0][1] is None else torch.cat([p[1] for p in parts], dim=1)]
     if want_radii:
@@ -208,7 +221,7 @@ def render_views(
 
 def _render_views_once(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means, gaussian_covariances,
                        gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode, want_radii, count_work,
-                       grad_reducer=None):
+                       grad_reducer=None, mse=None):
     B, V = extrinsics.shape[:2]
     h, w = image_shape
     dev = gaussian_means.device
@@ -225,6 +238,9 @@ def _render_views_once(extrinsics, intrinsics, near, far, image_shape, backgroun
 
     pack = ViewPack(scene_index, view, full, campos, tanfov, bg, h, w, scale_pack, depth_mode, depth_affine, depth_clamp,
                     grad_reducer)
+    if mse is not None:
+        pack.mse_target = mse["target"].reshape(B * V, 3, h, w)
+        pack.mse_weight, pack.mse_l1, pack.mse_count = float(mse["weight"]), bool(mse.get("l1", False)), int(mse["count"])
     if use_sh:
         degree = isqrt(gaussian_sh_coefficients.shape[-1]) - 1
         colors = gaussian_sh_coefficients
@@ -235,6 +251,8 @@ def _render_views_once(extrinsics, intrinsics, near, far, image_shape, backgroun
                                     sh_degree=degree, sh_layout=_lib.SH_CHANNEL_MAJOR, want_radii=want_radii, count_work=count_work)
     color = color.reshape(B, V, 3, h, w)
     depth = None if depth is None else depth.reshape(B, V, h, w)
+    if mse is not None:
+        mse["loss"], mse["sse_clipped"] = pack.mse_result[0], pack.mse_result[1].reshape(B, V)
     if want_radii:
         return color, depth, radii.reshape(B, V, -1)
     return color, depth

@@ -247,11 +247,18 @@ class ViewShardedDecoder(torch.nn.Module):
     (inference); otherwise the local slice (training: the loss is computed on the local views)."""
 
     def __init__(self, decoder: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, gather: bool = False,
-                 fused_reduce: bool = False, overlap_reduce: bool = False, nvls_reduce: bool = False):
+                 fused_reduce: bool = False, overlap_reduce: bool = False, nvls_reduce: bool = False, scatter_grads: bool = False,
+                 pieces: int = 4):
         super().__init__()
         self.decoder = decoder
         self.group = group
         self.gather = gather
+        # scatter_grads: REDUCE-SCATTER instead of all-reduce -- every rank gets the summed gradient of its own Gaussian range
+        # (range_bounds) and zeros elsewhere, pulled out of the NVSwitch in pieces under the projection backward
+        if scatter_grads and dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(decoder, "grad_reducer"):
+            self.reducer = RangeScatterReducer(group, pieces)
+            decoder.grad_reducer = self.reducer
+            return
         # nvls_reduce: gradients land in symmetric memory and are summed in place by the library's NVLS kernel
         if nvls_reduce and dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(decoder, "grad_reducer"):
             self.reducer = NvlsAllReducer(group)
@@ -303,8 +310,10 @@ def range_bounds(num_gaussians: int, world_size: int, rank: int) -> tuple[int, i
 class RangeScatterReducer:
     """Reduce-scatter of the per-Gaussian gradients by the library's own NVLS kernel, overlapped with the projection
     backward (see above).  The backward writes its gradients (ordinary stores) into one buffer of torch symmetric memory;
-    ``ROTATE`` buffers alternate.  The tensors it hands out have the full shape, but only this rank's Gaussian range holds
-    the cross-rank sum -- ``_GatherRanges.backward`` returns exactly that range."""
+    ``ROTATE`` buffers alternate.  The tensors it hands out have the full shape: this rank's Gaussian range holds the sum over
+    all ranks, the rest is zero -- so the sum over the ranks of what the ranks get IS the all-reduced gradient (a replicated
+    encoder can backpropagate just that on every rank: its parameter gradients are summed over the ranks anyway), and
+    ``_GatherRanges.backward`` returns exactly the range."""
 
     scatter = True
     ROTATE = 3
@@ -315,6 +324,7 @@ class RangeScatterReducer:
         self.rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         self.num_pieces = max(1, int(pieces))
         self._bufs = {}
+        self._outs = {}
         self._turn = 0
         self._side = None
         self.available = self.world > 1 and torch.cuda.is_available()
@@ -342,14 +352,23 @@ class RangeScatterReducer:
                 ring.append((t, h))
             self._bufs[key] = ring
         if self._side is None:
-            self._side = torch.cuda.Stream(device)
+            # high priority: the pulls and their barriers are small kernels that must get SM slots while the next piece of the
+            # projection backward (tens of thousands of CTAs) is queueing for the same SMs
+            self._side = torch.cuda.Stream(device, priority=-1)
         self._turn = (self._turn + 1) % self.ROTATE
         self._cur = self._bufs[key][self._turn]
         self._piece = 0
         buf = self._cur[0]
+        # results: a local (non-symmetric) buffer per rotation slot, zero outside this rank's range for good -- only the
+        # range is ever written, by the pulls.  Summed over the ranks, the tensors handed out are the all-reduced gradient.
+        okey = (o, device, self._turn)
+        if okey not in self._outs:
+            self._outs[okey] = torch.zeros(o, dtype=torch.float32, device=device)
+        self._out = self._outs[okey]
+        self._views = lambda flat: [flat[a:a + n].view(s) for a, n, s in zip(offs, sizes, shapes)]
         # the side stream's previous pulls (of an older buffer) are long done; order it behind the current stream once
         self._side.wait_stream(torch.cuda.current_stream(device))
-        return [buf[a:a + n].view(s) for a, n, s in zip(offs, sizes, shapes)]
+        return self._views(buf)
 
     def pieces(self):
         """(chunk_begin, chunk_count, chunk_stride, chunk_repeat) of every piece of the projection backward."""
@@ -392,12 +411,14 @@ class RangeScatterReducer:
                 part = segs[i:i + 16]
                 so = (C.c_ulonglong * len(part))(*[p[0] for p in part])
                 sn = (C.c_ulonglong * len(part))(*[p[1] for p in part])
-                _lib.check(L.b200s_nvls_reduce_segments(h.multicast_ptr, buf.data_ptr(), so, sn, len(part), self._side.cuda_stream),
+                _lib.check(L.b200s_nvls_reduce_segments(h.multicast_ptr, self._out.data_ptr(), so, sn, len(part), self._side.cuda_stream),
                            "b200s_nvls_reduce_segments")
 
     def end(self):
+        """-> the gradient tensors: this rank's Gaussian range summed over all ranks, zero elsewhere."""
         buf, _ = self._cur
         torch.cuda.current_stream(buf.device).wait_stream(self._side)
+        return self._views(self._out)
 
 
 class _GatherRanges(torch.autograd.Function):

@@ -45,6 +45,11 @@ class ViewPack:
     depth_affine: Optional[torch.Tensor] = None  # [VV,4]
     depth_clamp: Optional[torch.Tensor] = None   # [VV,2]
     grad_reducer: Optional[object] = None        # dist.FusedGradReducer: sum the gradients over ranks inside the kernel
+    mse_target: Optional[torch.Tensor] = None    # [VV,3,H,W] ground truth: fuse weight * mean((color - target)^2) into the forward
+    mse_weight: float = 1.0
+    mse_l1: bool = False                         # mean absolute error instead (l1_loss=True of loss_mse.py:41-43)
+    mse_count: Optional[int] = None              # colour values the mean runs over (default: those of this call; view-sharded
+                                                 # callers pass the count over all ranks)
 
 
 @dataclass
@@ -246,8 +251,17 @@ class _Rasterize(torch.autograd.Function):
             return _Rasterize._forward(ctx, means, covs, colors, opacities, means2d, vp, use_sh, sh_degree, sh_layout, want_radii, count_work)
 
     @staticmethod
-    def backward(ctx, g_color, g_depth, _g_radii):
+    def backward(ctx, g_color, g_depth, _g_radii, g_loss=None, _g_sse=None):
         with torch.cuda.device(ctx.saved_tensors[0].device):
+            color_scale = None
+            if g_loss is not None and ctx.mse_grad is not None:
+                # the fused loss: its dL/dcolor was written by the forward epilogue, and the upstream gradient of the loss (a
+                # device scalar) is applied by the backward kernel as it loads the pixel -- no pass over the images, no sync
+                if g_color is None:
+                    g_color, color_scale = ctx.mse_grad, g_loss.to(torch.float32).reshape(1).contiguous()
+                else:  # the caller ALSO used the colour
+                    g_color = g_color + ctx.mse_grad * g_loss
+            ctx.color_scale = color_scale
             return _Rasterize._backward(ctx, g_color, g_depth, _g_radii)
 
     @staticmethod
@@ -268,6 +282,17 @@ class _Rasterize(torch.autograd.Function):
             _status_ring = _HostStatusRing()
         slot, slot_ptr = _status_ring.take()
         out = _lib.Out(_ptr(color), _ptr(depth), _ptr(radii), 1 if count_work else 0, slot_ptr)
+        mse_grad = mse_partials = None
+        if vp.mse_target is not None:
+            tgt = _f32c(vp.mse_target, "mse_target")
+            if tgt.shape != (VV, 3, H, W):
+                raise ValueError(f"mse_target must be [{VV},3,{H},{W}], got {tuple(tgt.shape)}")
+            tiles = ((H + 15) // 16) * ((W + 15) // 16)
+            mse_grad = torch.empty_like(color)
+            mse_partials = torch.empty((VV, tiles, 2), dtype=torch.float32, device=dev)
+            out.mse_target, out.mse_grad, out.mse_partials = _ptr(tgt), _ptr(mse_grad), _ptr(mse_partials)
+            out.mse_scale = float(vp.mse_weight) / float(vp.mse_count or VV * 3 * H * W)
+            out.mse_l1 = 1 if vp.mse_l1 else 0
 
         key = (dev.index, B, N, VV, H, W)
         _drain_pending(block=False)
@@ -332,6 +357,15 @@ class _Rasterize(torch.autograd.Function):
             debug_last = dict(plan=plan, saved=saved, scratch=scratch, num_pairs=num_pairs, N=N, VV=VV, H=H, W=W)
         ctx.save_for_backward(means, covs, colors, opacities)
         ctx.b200 = (vp, use_sh, sh_degree, sh_layout, plan, lease, means2d is not None, pending)
+        ctx.set_materialize_grads(False)
+        ctx.mse_grad = mse_grad
+        if mse_partials is not None:
+            sums = mse_partials.sum(dim=1)                       # [VV, 2], fixed order
+            loss = sums[:, 0].sum() * out.mse_scale              # weight * mean(...)
+            sse_clipped = sums[:, 1]                             # per view, for the PSNR
+        else:
+            loss = color.new_empty(0)
+            sse_clipped = color.new_empty(0)
         outs = [color]
         if depth is not None:
             outs.append(depth)
@@ -340,8 +374,10 @@ class _Rasterize(torch.autograd.Function):
             ctx.mark_non_differentiable(outs[-1])
         if radii is None:
             radii = torch.empty(0, dtype=torch.int32, device=dev)
-        ctx.mark_non_differentiable(radii)
-        return outs[0], outs[1], radii
+        ctx.mark_non_differentiable(radii, sse_clipped)
+        if mse_partials is None:
+            ctx.mark_non_differentiable(loss)
+        return outs[0], outs[1], radii, loss, sse_clipped
 
     @staticmethod
     def _backward(ctx, g_color, g_depth, _g_radii):
@@ -364,7 +400,7 @@ class _Rasterize(torch.autograd.Function):
             g_depth = None
         d_m2d = torch.empty((VV, N, 3), dtype=torch.float32, device=dev) if want_m2d else None
         scratch = _scratch(dev, plan.scratch_bytes)
-        gout = _lib.GradOut(_ptr(g_color), _ptr(g_depth))
+        gout = _lib.GradOut(_ptr(g_color), _ptr(g_depth), _ptr(getattr(ctx, "color_scale", None)))
         reducer = vp.grad_reducer if (vp.grad_reducer is not None and getattr(vp.grad_reducer, "available", False)) else None
         out = _lib.Out(None, None, None, 0)
 
@@ -383,7 +419,7 @@ class _Rasterize(torch.autograd.Function):
             for pc in reducer.pieces():
                 call(mk(2, pc))
                 reducer.piece_done(pc)
-            reducer.end()
+            d_means, d_covs, d_colors, d_op = reducer.end()
         elif reducer is not None and getattr(reducer, "in_place", False):
             # outputs are views of a symmetric-memory buffer; the reducer sums it over the ranks in place afterwards
             d_means, d_covs, d_colors, d_op = reducer.begin([means.shape, covs.shape, colors.shape, opacities.shape], dev)
@@ -464,6 +500,8 @@ def rasterize(means: torch.Tensor, covariances: torch.Tensor, colors: torch.Tens
         sh_degree = 0
     if N == 0 or views.scene_index.shape[0] == 0:
         raise ValueError("empty scene or view list")
-    color, depth, radii = _Rasterize.apply(means, covariances, colors, opacities, means2d, views, use_sh, sh_degree, sh_layout,
-                                           want_radii, count_work)
+    color, depth, radii, loss, sse = _Rasterize.apply(means, covariances, colors, opacities, means2d, views, use_sh, sh_degree, sh_layout,
+                                                      want_radii, count_work)
+    if views.mse_target is not None:
+        views.mse_result = (loss, sse)
     return color, (depth if views.depth_mode is not None else None), (radii if want_radii else None)

@@ -25,3 +25,9 @@ class Gaussians:
 class DecoderOutput:
     color: Tensor            # [batch, view, 3, height, width]
     depth: Optional[Tensor]  # [batch, view, height, width] or None
+
+
+@dataclass
+class FusedDecoderOutput(DecoderOutput):
+    """DecoderOutput plus what the compositing epilogue computed against a target image (loss_mse.FusedMse)."""
+    fused_mse: Optional[object] = None
