@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 9
+#define B200S_ABI_VERSION 10
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -61,6 +61,20 @@ typedef struct B200sScene {
   const float* harmonics;      /* [B,N,3,d_sh] or [B,N,d_sh,3]; NULL when colors_precomp is used */
   const float* colors_precomp; /* [B,N,3] or NULL (use_sh=False path, cuda_splatting.py:117) */
   const float* opacities;      /* [B,N] */
+  /* Optional -- the Gaussians as the encoder head's RAW output, with the Gaussian adapter
+   * (src/model/encoder/common/gaussian_adapter.py:49-102, gaussians.py:8-44, src/misc/sh_rotation.py:10-30) fused into the
+   * projection.  When raw_head != NULL the five tensor pointers above are ignored and must be NULL,
+   * num_gaussians must equal raw_views * raw_h * raw_w (order (view, y, x)), raw_h * raw_w must be a multiple of 256, and
+   * sh_degree / sh_coeffs must be 2 / 9.  The world-space tensors are never materialised. */
+  const float* raw_head;   /* [B, raw_views, 37, raw_h*raw_w] channel planes of the head: opacity logit | 2 xy-offset logits |
+                              3 scales | quaternion xyzw | 27 SH (channel-major 3 x 9) */
+  const float* raw_depth;  /* [B, raw_views, raw_h*raw_w] */
+  const float* raw_image;  /* [B, raw_views, 3, raw_h*raw_w] context images (SH DC initialisation, gaussian_adapter.py:78-83) */
+  const float* raw_camera; /* [B, raw_views, 56] per context view: camera-to-world rotation (9, row-major) | translation (3) |
+                              inverse intrinsics (9) | pad | degree-2 SH rotation (25) | SH mask (9) */
+  int32_t raw_views, raw_h, raw_w;
+  float raw_scale_min, raw_scale_max;  /* gaussian_scale_min / gaussian_scale_max */
+  float* raw_cooked_out;   /* optional (tests): [B,N,40] = mean 3 | covariance 3x3 | opacity | harmonics 3x9 as the kernel built them */
 } B200sScene;
 
 /* The views: VV = total number of (scene, target camera) pairs rendered by this call. */
@@ -198,6 +212,8 @@ typedef struct B200sGradIn { /* all fp32, OVERWRITTEN (summed over the views of 
   int32_t chunk_stride;   /* with chunk_repeat > 1 the launch covers the chunks chunk_begin + r * chunk_stride + k, r < chunk_repeat, */
   int32_t chunk_repeat;   /* k < chunk_count (clipped to the scene): the j-th piece of EVERY rank's Gaussian range in one launch,
                              so that all ranks can pull their share of it (reduce-scatter) while the next piece is computed */
+  float* dL_draw_head;    /* raw scenes: [B, raw_views, 37, raw_h*raw_w] gradient w.r.t. the head's channel planes ... */
+  float* dL_draw_depth;   /* ... and [B, raw_views, raw_h*raw_w] w.r.t. the depth (the five tensor gradients above are then unused) */
 } B200sGradIn;
 
 /* Reduce-scatter building block over an NVSwitch domain: for each of the nseg (<= 16) segments -- seg_offset[i] floats into a

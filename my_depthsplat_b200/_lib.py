@@ -10,7 +10,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200splat.so"
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 B200S_OK, B200S_EBADARG, B200S_ECUDA = 0, 1, 3
 COV_3X3, COV_UPPER6 = 0, 1
@@ -26,6 +26,9 @@ class Scene(C.Structure):
         ("num_scenes", C.c_int32), ("num_gaussians", C.c_int32), ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
         ("cov_layout", C.c_int32), ("sh_layout", C.c_int32),
         ("means", _f32p), ("covariances", _f32p), ("harmonics", _f32p), ("colors_precomp", _f32p), ("opacities", _f32p),
+        ("raw_head", _f32p), ("raw_depth", _f32p), ("raw_image", _f32p), ("raw_camera", _f32p),
+        ("raw_views", C.c_int32), ("raw_h", C.c_int32), ("raw_w", C.c_int32), ("raw_scale_min", C.c_float), ("raw_scale_max", C.c_float),
+        ("raw_cooked_out", _f32p),
     ]
 
 
@@ -81,7 +84,7 @@ class GradIn(C.Structure):
         ("dL_dmeans", _f32p), ("dL_dcovariances", _f32p), ("dL_dharmonics", _f32p), ("dL_dcolors", _f32p),
         ("dL_dopacities", _f32p), ("dL_dmeans2D", _f32p), ("multicast", C.c_int32),
         ("stages", C.c_int32), ("chunk_begin", C.c_int32), ("chunk_count", C.c_int32), ("chunk_stride", C.c_int32),
-        ("chunk_repeat", C.c_int32),
+        ("chunk_repeat", C.c_int32), ("dL_draw_head", _f32p), ("dL_draw_depth", _f32p),
     ]
 
 

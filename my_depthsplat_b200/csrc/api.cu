@@ -184,8 +184,16 @@ int b200s_plan(const B200sDims* d, B200sPlan* p) {
 static int check_common(const B200sScene* sc, const B200sViews* vw, const B200sPlan* pl, const void* saved, const void* scratch) {
   if (!sc || !vw || !pl || !saved || !scratch) return B200S_EBADARG;
   if (pl->abi_version != B200S_ABI_VERSION) return B200S_EBADARG;
+  if (sc->raw_head) {  // raw scenes: the adapter runs inside the projection
+    if (sc->means || sc->covariances || sc->opacities || sc->harmonics || sc->colors_precomp) return B200S_EBADARG;
+    if (!sc->raw_depth || !sc->raw_image || !sc->raw_camera) return B200S_EBADARG;
+    if (sc->raw_views <= 0 || sc->raw_h <= 0 || sc->raw_w <= 0 || (sc->raw_h * sc->raw_w) % PRE_THREADS != 0) return B200S_EBADARG;
+    if ((long long)sc->raw_views * sc->raw_h * sc->raw_w != sc->num_gaussians || sc->sh_degree != 2 || sc->sh_coeffs != 9) return B200S_EBADARG;
+    if (((uintptr_t)sc->raw_head | (uintptr_t)sc->raw_depth | (uintptr_t)sc->raw_image) & 15) return B200S_EBADARG;
+  } else {
   if (!sc->means || !sc->covariances || !sc->opacities) return B200S_EBADARG;
   if (!sc->harmonics && !sc->colors_precomp) return B200S_EBADARG;
+  }
   if (!sc->colors_precomp) {
     if (sc->sh_degree < 0 || sc->sh_degree > 3) return B200S_EBADARG;
     if (sc->sh_coeffs < (sc->sh_degree + 1) * (sc->sh_degree + 1) || sc->sh_coeffs > 16) return B200S_EBADARG;
@@ -261,9 +269,14 @@ int b200s_backward(const B200sScene* sc, const B200sViews* vw, const B200sPlan* 
                    const B200sGradOut* gout, const B200sGradIn* gin, void* stream_) {
   const int rc = check_common(sc, vw, pl, saved_, scratch_);
   if (rc != B200S_OK) return rc;
-  if (!gout || !gin || !gout->dL_dcolor || !gin->dL_dmeans || !gin->dL_dcovariances || !gin->dL_dopacities) return B200S_EBADARG;
+  if (!gout || !gin || !gout->dL_dcolor) return B200S_EBADARG;
   if (vw->depth_mode != B200S_DEPTH_NONE && !gout->dL_ddepth) return B200S_EBADARG;
-  if (sc->colors_precomp ? !gin->dL_dcolors : !gin->dL_dharmonics) return B200S_EBADARG;
+  if (sc->raw_head) {
+    if (!gin->dL_draw_head || !gin->dL_draw_depth) return B200S_EBADARG;
+  } else {
+    if (!gin->dL_dmeans || !gin->dL_dcovariances || !gin->dL_dopacities) return B200S_EBADARG;
+    if (sc->colors_precomp ? !gin->dL_dcolors : !gin->dL_dharmonics) return B200S_EBADARG;
+  }
   (void)fwd_out;
   const char* saved = (const char*)saved_; char* scratch = (char*)scratch_;
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -21,6 +21,7 @@
 //
 // HBM-bound: per (view, Gaussian) 148 B read (L2-shared across views) + 72 B written, + 8 B read and
 // 12 B per pair written by the emission.
+#include "adapter.cuh"
 #include "kernels.cuh"
 
 namespace b200s {
@@ -92,10 +93,14 @@ __device__ __forceinline__ float eval_sh_channel(int deg, const float* sh, int k
   return r;
 }
 
-// SPECIALISED = the layout DepthSplat hands over (3x3 covariances, SH [N,3,9] channel-major, degree 2):
-// every stride is a compile-time constant.  The generic instantiation takes them from the arguments.
-template <bool SPECIALISED>
+// MODE 1 (specialised) = the layout DepthSplat hands over (3x3 covariances, SH [N,3,9] channel-major, degree 2): every
+// stride is a compile-time constant.  MODE 0 (generic) takes them from the arguments.  MODE 2 (raw) = the encoder head's
+// raw channel planes: the Gaussian adapter runs here, on the staged chunk (adapter.cuh), and the specialised layout is
+// what it leaves in shared memory / registers -- the rest of the kernel is the same.
+template <int MODE>
 __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScene sc, const B200sViews vw, const PreArgs a) {
+  constexpr bool SPECIALISED = MODE != 0;
+  constexpr bool RAW = MODE == 2;
   extern __shared__ __align__(16) float smem[];
   __shared__ ViewParams vp;
   __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
@@ -121,6 +126,47 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
   float* s_op = s_cov + PRE_THREADS * cov_floats;        // [256]
   float* s_col = s_op + PRE_THREADS;                     // [256*col_stride]
   float4* s_rec = reinterpret_cast<float4*>(s_col + PRE_THREADS * col_stride);  // [256*4] record staging
+  float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, opac = 0.f;
+  if (RAW) {
+    // ---- stage the 41 raw planes of the chunk (37 head channels, depth, 3 image channels), run the adapter -----------
+    __shared__ RawCam s_cam;
+    const int hw = sc.raw_h * sc.raw_w;
+    const int cv = i0 / hw, p0 = i0 - cv * hw;           // context view and first pixel of the chunk (hw % 256 == 0)
+    const size_t sv = (size_t)scene * sc.raw_views + cv;
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      mbar_expect_tx(&s_bar, (uint32_t)(RAW_PLANES * PRE_THREADS * 4));
+      for (int ch = 0; ch < RAW_CH; ch++) tma_bulk_load(smem + ch * PRE_THREADS, sc.raw_head + (sv * RAW_CH + ch) * hw + p0, PRE_THREADS * 4, &s_bar);
+      tma_bulk_load(smem + RAW_CH * PRE_THREADS, sc.raw_depth + sv * hw + p0, PRE_THREADS * 4, &s_bar);
+      for (int ch = 0; ch < 3; ch++) tma_bulk_load(smem + (RAW_CH + 1 + ch) * PRE_THREADS, sc.raw_image + (sv * 3 + ch) * hw + p0, PRE_THREADS * 4, &s_bar);
+    }
+    if (tid < RAW_CAM_FLOATS) reinterpret_cast<float*>(&s_cam)[tid] = __ldg(sc.raw_camera + sv * RAW_CAM_FLOATS + tid);
+    __syncthreads();  // the barrier is initialised (and the camera block staged) before anyone waits
+    mbar_wait(&s_bar, 0);
+    float h[RAW_CH], img[3];
+#pragma unroll
+    for (int ch = 0; ch < RAW_CH; ch++) h[ch] = smem[ch * PRE_THREADS + tid];
+    const float depth = smem[RAW_CH * PRE_THREADS + tid];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) img[ch] = smem[(RAW_CH + 1 + ch) * PRE_THREADS + tid];
+    __syncthreads();  // every raw value is in registers: the specialised layout may now overwrite the planes
+    const int p = p0 + tid;
+    Cooked g;
+    cook(h, depth, s_cam, p % sc.raw_w, p / sc.raw_w, sc.raw_w, sc.raw_h, sc.raw_scale_min, sc.raw_scale_max, g);
+    mraw[0] = g.mean[0]; mraw[1] = g.mean[1]; mraw[2] = g.mean[2];
+#pragma unroll
+    for (int k = 0; k < 6; k++) craw[k] = g.cov[k];
+    opac = g.op;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) cook_sh(h + 10 + 9 * ch, img[ch], s_cam, s_col + tid * 27 + 9 * ch);
+    if (sc.raw_cooked_out) {  // tests: the world-space Gaussian as built here
+      float* o = sc.raw_cooked_out + (g0 + tid) * 40;
+      o[0] = g.mean[0]; o[1] = g.mean[1]; o[2] = g.mean[2];
+      o[3] = g.cov[0]; o[4] = g.cov[1]; o[5] = g.cov[2]; o[6] = g.cov[1]; o[7] = g.cov[3]; o[8] = g.cov[4]; o[9] = g.cov[2]; o[10] = g.cov[4]; o[11] = g.cov[5];
+      o[12] = g.op;
+      for (int k = 0; k < 27; k++) o[13 + k] = s_col[tid * 27 + k];
+    }
+  } else {
   const float* col_src = precomp ? sc.colors_precomp : sc.harmonics;
   {
     const float* g_mean = sc.means + g0 * 3; const float* g_cov = sc.covariances + g0 * cov_floats;
@@ -148,7 +194,6 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
       __syncthreads();
     }
   }
-  float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, opac = 0.f;
   if (tid < n) {
     mraw[0] = s_mean[tid * 3]; mraw[1] = s_mean[tid * 3 + 1]; mraw[2] = s_mean[tid * 3 + 2];
     const float* cp = s_cov + tid * cov_floats;
@@ -159,6 +204,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
       craw[0] = cp[0]; craw[1] = cp[1]; craw[2] = cp[2]; craw[3] = cp[4]; craw[4] = cp[5]; craw[5] = cp[8];
     }
     opac = s_op[tid];
+  }
   }
   const float* cs = s_col + tid * col_stride;
 
@@ -555,6 +601,8 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   a.col_floats = sc.colors_precomp ? 3 : 3 * sc.sh_coeffs;
   a.col_stride = a.col_floats | 1;
   a.fpg = 3 + a.cov_floats + 1 + a.col_stride;
+  // raw scenes: the 41 staged planes (41 KB) share the specialised layout's 40 KB + record staging (they are dead before the records are written)
+  if (sc.raw_head) { a.cov_floats = 9; a.col_floats = 27; a.col_stride = 27; a.fpg = 40; }
   a.rec = reinterpret_cast<Rec*>(saved + plan.off_rec);
   // the sort ping-pongs `sort_passes` times and must end in the A buffers
   const bool start_in_a = (plan.sort_passes % 2) == 0;
@@ -584,17 +632,19 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   if (binned) { if ((e = cudaMemsetAsync(a.bin_count, 0, (size_t)plan.bins * sizeof(uint32_t), stream)) != cudaSuccess) return e; }
   else if ((e = cudaMemsetAsync(a.hist, 0, 8 * 256 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
   const size_t smem = (size_t)PRE_THREADS * a.fpg * sizeof(float) + (size_t)PRE_THREADS * sizeof(Rec);
-  const bool specialised = sc.cov_layout == B200S_COV_3X3 && !sc.colors_precomp && sc.sh_layout == B200S_SH_CHANNEL_MAJOR &&
-                           sc.sh_coeffs == 9 && sc.sh_degree == 2;
+  const bool raw = sc.raw_head != nullptr;
+  const bool specialised = raw || (sc.cov_layout == B200S_COV_3X3 && !sc.colors_precomp && sc.sh_layout == B200S_SH_CHANNEL_MAJOR &&
+                                   sc.sh_coeffs == 9 && sc.sh_degree == 2);
   // the attribute is per (function, device) and cheap to set: no cache that a second device or thread could get wrong
   if (smem > 48 * 1024) {
-    if ((e = cudaFuncSetAttribute(specialised ? (const void*)project_kernel<true> : (const void*)project_kernel<false>,
+    if ((e = cudaFuncSetAttribute(raw ? (const void*)project_kernel<2> : (specialised ? (const void*)project_kernel<1> : (const void*)project_kernel<0>),
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
   }
   if (plan.pre_tickets > 0) {
     const int proj_blocks = a.chunks * sc.num_scenes;
-    if (specialised) project_kernel<true><<<proj_blocks, PRE_THREADS, smem, stream>>>(sc, vw, a);
-    else project_kernel<false><<<proj_blocks, PRE_THREADS, smem, stream>>>(sc, vw, a);
+    if (raw) project_kernel<2><<<proj_blocks, PRE_THREADS, smem, stream>>>(sc, vw, a);
+    else if (specialised) project_kernel<1><<<proj_blocks, PRE_THREADS, smem, stream>>>(sc, vw, a);
+    else project_kernel<0><<<proj_blocks, PRE_THREADS, smem, stream>>>(sc, vw, a);
     const int sms = device_sm_count();
     const int walk_blocks = plan.pre_tickets < sms * 8 ? plan.pre_tickets : sms * 8;
     if (binned) {

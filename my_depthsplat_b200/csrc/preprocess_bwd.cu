@@ -10,6 +10,7 @@
 // No atomics; the order of the sum over views is fixed (ascending view index).
 //
 // HBM-bound: per Gaussian 148 B in + 148 B out, plus (48 + 16) B per (view, Gaussian).
+#include "adapter.cuh"
 #include "kernels.cuh"
 
 namespace b200s {
@@ -71,7 +72,9 @@ __device__ __forceinline__ void dnormvdv(const float v[3], const float dv[3], fl
 }
 
 // NC = SH coefficients per channel that are ACTIVE ((deg+1)^2); NC == 0 -> colors_precomp path.
-template <int NC, bool MC>
+// RAW = the scene is the encoder head's raw output (adapter.cuh): the chunk's Gaussians are rebuilt from the raw planes as
+// in the forward, and the accumulated gradients go through the adapter's chain rule before they are written.
+template <int NC, bool MC, bool RAW = false>
 __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B200sScene sc, const B200sViews vw, const B200sGradIn gin,
                                                                      const PreBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -92,6 +95,44 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
   float* s_mean = smem;
   float* s_cov = s_mean + PRE_THREADS * 3;
   float* s_col = s_cov + PRE_THREADS * a.cov_floats;
+  float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float op = 0.f;
+  __shared__ RawCam s_cam;
+  float hraw[RAW ? 10 : 1];   // the ten geometry channels (the chain rule needs them again)
+  Cooked ck;
+  int raw_cv = 0, raw_p0 = 0;
+  if (RAW) {
+    const int hw = sc.raw_h * sc.raw_w;
+    raw_cv = i0 / hw; raw_p0 = i0 - raw_cv * hw;
+    const size_t sv = (size_t)scene * sc.raw_views + raw_cv;
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      mbar_expect_tx(&s_bar, (uint32_t)(RAW_PLANES * PRE_THREADS * 4));
+      for (int ch = 0; ch < RAW_CH; ch++) tma_bulk_load(smem + ch * PRE_THREADS, sc.raw_head + (sv * RAW_CH + ch) * hw + raw_p0, PRE_THREADS * 4, &s_bar);
+      tma_bulk_load(smem + RAW_CH * PRE_THREADS, sc.raw_depth + sv * hw + raw_p0, PRE_THREADS * 4, &s_bar);
+      for (int ch = 0; ch < 3; ch++) tma_bulk_load(smem + (RAW_CH + 1 + ch) * PRE_THREADS, sc.raw_image + (sv * 3 + ch) * hw + raw_p0, PRE_THREADS * 4, &s_bar);
+    }
+    if (tid < RAW_CAM_FLOATS) reinterpret_cast<float*>(&s_cam)[tid] = __ldg(sc.raw_camera + sv * RAW_CAM_FLOATS + tid);
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+    float h[RAW_CH], img[3];
+#pragma unroll
+    for (int ch = 0; ch < RAW_CH; ch++) h[ch] = smem[ch * PRE_THREADS + tid];
+    const float depth = smem[RAW_CH * PRE_THREADS + tid];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) img[ch] = smem[(RAW_CH + 1 + ch) * PRE_THREADS + tid];
+    __syncthreads();  // every raw value is in registers: the rotated SH may now overwrite the planes
+    const int p = raw_p0 + tid;
+    cook(h, depth, s_cam, p % sc.raw_w, p / sc.raw_w, sc.raw_w, sc.raw_h, sc.raw_scale_min, sc.raw_scale_max, ck);
+    mraw[0] = ck.mean[0]; mraw[1] = ck.mean[1]; mraw[2] = ck.mean[2];
+#pragma unroll
+    for (int k = 0; k < 6; k++) craw[k] = ck.cov[k];
+    op = ck.op;
+#pragma unroll
+    for (int k = 0; k < (RAW ? 10 : 1); k++) hraw[k] = h[k];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) cook_sh(h + 10 + 9 * ch, img[ch], s_cam, s_col + tid * 27 + 9 * ch);
+  } else {
   {
     const float* g_mean = sc.means + g0 * 3; const float* g_cov = sc.covariances + g0 * a.cov_floats;
     const float* g_col = NC > 0 ? sc.harmonics + g0 * a.col_floats : nullptr;
@@ -114,14 +155,13 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
       __syncthreads();
     }
   }
-
-  float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const float op = tid < n ? __ldg(sc.opacities + g0 + tid) : 0.f;
+  op = tid < n ? __ldg(sc.opacities + g0 + tid) : 0.f;
   if (tid < n) {
     mraw[0] = s_mean[tid * 3]; mraw[1] = s_mean[tid * 3 + 1]; mraw[2] = s_mean[tid * 3 + 2];
     const float* cp = s_cov + tid * a.cov_floats;
     if (a.cov_floats == 6) { for (int k = 0; k < 6; k++) craw[k] = cp[k]; }
     else { craw[0] = cp[0]; craw[1] = cp[1]; craw[2] = cp[2]; craw[3] = cp[4]; craw[4] = cp[5]; craw[5] = cp[8]; }
+  }
   }
   const int cstride = (sc.sh_layout == B200S_SH_CHANNEL_MAJOR) ? sc.sh_coeffs : 1;
   const int kstride = (sc.sh_layout == B200S_SH_CHANNEL_MAJOR) ? 1 : 3;
@@ -290,6 +330,25 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
     }
   }
 
+  if (RAW) {
+    // ---- the adapter's chain rule; one value per (channel plane, pixel): consecutive threads write consecutive addresses ----
+    const int hw = sc.raw_h * sc.raw_w;
+    const size_t sv = (size_t)scene * sc.raw_views + raw_cv;
+    float dh[10], ddepth;
+    cook_backward(hraw, s_cam, ck, sc.raw_w, sc.raw_h, sc.raw_scale_min, sc.raw_scale_max, dmean, dcov, dop, dh, ddepth);
+    float* dst = gin.dL_draw_head + sv * RAW_CH * hw + raw_p0 + tid;
+#pragma unroll
+    for (int k = 0; k < 10; k++) dst[(size_t)k * hw] = dh[k];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      float din[9];
+      cook_sh_backward(dcol + ch * NC, s_cam, din);
+#pragma unroll
+      for (int k = 0; k < 9; k++) dst[(size_t)(10 + 9 * ch + k) * hw] = din[k];
+    }
+    gin.dL_draw_depth[sv * hw + raw_p0 + tid] = ddepth;
+    return;
+  }
   // ---- coalesced writes through shared memory ------------------------------------------------------
   __syncthreads();
   float* s_dmean = smem;
@@ -331,6 +390,7 @@ cudaError_t launch_preprocess_bwd(const B200sScene& sc, const B200sViews& vw, co
   a.cov_floats = sc.cov_layout == B200S_COV_UPPER6 ? 6 : 9;
   a.col_floats = sc.colors_precomp ? 3 : 3 * sc.sh_coeffs;
   a.col_stride = a.col_floats | 1;
+  if (sc.raw_head) { a.cov_floats = 9; a.col_floats = 27; a.col_stride = 27; }
   a.rec = reinterpret_cast<const Rec*>(saved + plan.off_rec);
   a.grad_rec = reinterpret_cast<const float*>(scratch + plan.off_grad_rec);
   a.dL_dmeans2D = gin.dL_dmeans2D;
@@ -345,7 +405,7 @@ cudaError_t launch_preprocess_bwd(const B200sScene& sc, const B200sViews& vw, co
   if (a.chunk_repeat > 1 && (a.chunk_stride < a.chunk_count || a.chunk_count <= 0)) return cudaErrorInvalidValue;
   const int blocks = a.chunk_count * a.chunk_repeat * sc.num_scenes;
   if (blocks <= 0) return cudaSuccess;
-  const size_t smem = (size_t)PRE_THREADS * (3 + a.cov_floats + a.col_stride) * sizeof(float);
+  const size_t smem = sc.raw_head ? (size_t)PRE_THREADS * RAW_PLANES * sizeof(float) : (size_t)PRE_THREADS * (3 + a.cov_floats + a.col_stride) * sizeof(float);
   const int nc = sc.colors_precomp ? 0 : (sc.sh_degree + 1) * (sc.sh_degree + 1);
   cudaError_t e = cudaSuccess;
   stage_mark(B200S_STAGE_PRE_BWD, stream);
@@ -361,6 +421,13 @@ cudaError_t launch_preprocess_bwd(const B200sScene& sc, const B200sViews& vw, co
       if (e != cudaSuccess) return e;                                                                                      \
       preprocess_bwd_kernel<NCV, false><<<blocks, PRE_THREADS, smem, stream>>>(sc, vw, gin, a);                           \
     }                                                                                                                      \
+  }
+  if (sc.raw_head) {  // raw scenes: degree 2, no multicast variant
+    if (gin.multicast || nc != 9) return cudaErrorInvalidValue;
+    e = cudaFuncSetAttribute(preprocess_bwd_kernel<9, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    preprocess_bwd_kernel<9, false, true><<<blocks, PRE_THREADS, smem, stream>>>(sc, vw, gin, a);
+    return cudaGetLastError();
   }
   switch (nc) {
     case 0: LAUNCH(0); break;

@@ -258,6 +258,49 @@ def _render_views_once(extrinsics, intrinsics, near, far, image_shape, backgroun
     return color, depth
 
 
+def render_views_raw(
+    extrinsics: Tensor,            # [B,V,4,4] TARGET cameras, camera-to-world
+    intrinsics: Tensor,            # [B,V,3,3] normalised
+    near: Tensor,                  # [B,V]
+    far: Tensor,                   # [B,V]
+    image_shape: tuple[int, int],
+    background_color: Tensor,      # [3] or [B,V,3]
+    head: Tensor,                  # [B,Vc,37,h,w] raw channel planes of the encoder head
+    depth: Tensor,                 # [B,Vc,h,w]
+    context_images: Tensor,        # [B,Vc,3,h,w]
+    context_extrinsics: Tensor,    # [B,Vc,4,4]
+    context_intrinsics: Tensor,    # [B,Vc,3,3]
+    scale_min: float,
+    scale_max: float,
+    sh_mask: Tensor,               # [9]
+    depth_mode: Optional[DepthRenderingMode] = None,
+    cooked_out: Optional[Tensor] = None,
+):
+    """Encoder head output -> images, with the Gaussian adapter fused into the projection (see
+    gaussian_adapter.FusedAdapterDecoder).  Returns (color [B,V,3,H,W], depth [B,V,H,W] | None)."""
+    from .gaussian_adapter import sh_rotation_matrices
+    from .rasterizer import RawScene, rasterize_raw
+    B, V = extrinsics.shape[:2]
+    h, w = image_shape
+    Vc, hc, wc = head.shape[1], head.shape[3], head.shape[4]
+    dev = head.device
+    ext = extrinsics.reshape(B * V, 4, 4).to(torch.float32)
+    K = intrinsics.reshape(B * V, 3, 3).to(torch.float32)
+    near_f, far_f = near.reshape(B * V).to(torch.float32), far.reshape(B * V).to(torch.float32)
+    view, full, campos, tanfov, scale_pack, depth_affine, depth_clamp = _camera_tensors_cached(ext, K, near_f, far_f, depth_mode is not None, True)
+    bg = background_color.to(device=dev, dtype=torch.float32)
+    bg = bg.expand(B, V, 3).reshape(B * V, 3).contiguous() if bg.dim() == 1 else bg.reshape(B * V, 3).contiguous()
+    pack = ViewPack(_scene_index(dev, B, V), view, full, campos, tanfov, bg, h, w, scale_pack, depth_mode, depth_affine, depth_clamp)
+    # per context view: rotation | translation | K^-1 | pad | degree-2 SH rotation | SH mask
+    R = context_extrinsics[..., :3, :3].to(torch.float32)
+    cam = torch.cat([R.reshape(B, Vc, 9), context_extrinsics[..., :3, 3].to(torch.float32), context_intrinsics.to(torch.float32).inverse().reshape(B, Vc, 9),
+                     torch.zeros(B, Vc, 1, device=dev), sh_rotation_matrices(R, 2)[2].reshape(B, Vc, 25),
+                     sh_mask.to(device=dev, dtype=torch.float32).expand(B, Vc, 9)], dim=-1).contiguous()
+    raw = RawScene(Vc, hc, wc, scale_min, scale_max, context_images.reshape(B, Vc, 3, hc * wc), cam, cooked_out)
+    color, dimg, _ = rasterize_raw(head.reshape(B, Vc, 37, hc * wc), depth.reshape(B, Vc, hc * wc), raw, pack)
+    return color.reshape(B, V, 3, h, w), (None if dimg is None else dimg.reshape(B, V, h, w))
+
+
 def render_cuda(
     extrinsics: Tensor,                # [batch,4,4]
     intrinsics: Tensor,                # [batch,3,3]

@@ -52,24 +52,27 @@ class DecoderSplattingCUDA(Decoder[DecoderSplattingCUDACfg]):
                              persistent=False)
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
-                image_shape: tuple[int, int], depth_mode: Optional[DepthRenderingMode] = None, *,
-                mse_target: Optional[Tensor] = None, mse_weight: float = 1.0, mse_l1: bool = False,
-                mse_count: Optional[int] = None) -> DecoderOutput:
+                image_shape: tuple[int, int], depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
         """gaussians [B,N,...]; extrinsics [B,V,4,4]; intrinsics [B,V,3,3]; near/far [B,V] ->
-        DecoderOutput(color [B,V,3,H,W], depth [B,V,H,W] | None).
+        DecoderOutput(color [B,V,3,H,W], depth [B,V,H,W] | None)."""
+        color, depth = render_views(extrinsics, intrinsics, near, far, image_shape, self.background_color, gaussians.means,
+                                    gaussians.covariances, gaussians.harmonics, gaussians.opacities, depth_mode=depth_mode,
+                                    grad_reducer=self.grad_reducer)
+        return DecoderOutput(color, depth)
 
-        Extension (keyword-only): with ``mse_target`` [B,V,3,H,W] the result is a ``FusedDecoderOutput``
-        that also carries the MSE (or L1) loss of the colour against the target and the PSNR ingredients, computed in the
-        compositing epilogue; ``loss_mse.LossMse`` and ``loss_mse.compute_psnr`` pick them up."""
-        mse = None if mse_target is None else dict(target=mse_target, weight=mse_weight, l1=mse_l1)
-        if mse is not None and mse_count is not None:
+    def forward_fused_mse(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                          image_shape: tuple[int, int], depth_mode: Optional[DepthRenderingMode] = None, *, mse_target: Tensor,
+                          mse_weight: float = 1.0, mse_l1: bool = False, mse_count: Optional[int] = None) -> FusedDecoderOutput:
+        """``forward`` plus loss-side fusion: ``mse_target`` [B,V,3,H,W] is the ground truth the
+        reference's LossMse compares the colour with; the result also carries that loss (MSE, or L1) and the PSNR
+        ingredients, computed in the compositing epilogue.  ``loss_mse.LossMse`` and ``loss_mse.fused_psnr`` pick them up."""
+        from .loss_mse import FusedMse
+        mse = dict(target=mse_target, weight=mse_weight, l1=mse_l1)
+        if mse_count is not None:
             mse["count"] = mse_count
         color, depth = render_views(extrinsics, intrinsics, near, far, image_shape, self.background_color, gaussians.means,
                                     gaussians.covariances, gaussians.harmonics, gaussians.opacities, depth_mode=depth_mode,
                                     grad_reducer=self.grad_reducer, mse=mse)
-        if mse is None:
-            return DecoderOutput(color, depth)
-        from .loss_mse import FusedMse
         return FusedDecoderOutput(color, depth, FusedMse(mse["loss"], mse["sse_clipped"], mse_target, float(mse_weight), bool(mse_l1)))
 
     def render_depth(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,

@@ -1,6 +1,6 @@
 """The colour loss and PSNR the reference computes on the decoder's output -- src/loss/loss_mse.py:21-44 (``LossMse``),
 src/evaluation/metrics.py:11-19 (``compute_psnr``) -- with the same names, constructor and call signatures, plus the
-fused path of SURVEY.md 8f rank 3: when the decoder was given the target (``DecoderSplattingCUDA.forward(...,
+fused path of SURVEY.md 8f rank 3: when the decoder was given the target (``DecoderSplattingCUDA.forward_fused_mse(...,
 mse_target=...)``) the loss value, its dL/dcolor and the PSNR's squared error were produced by the compositing epilogue
 while every pixel was still in registers; ``LossMse.forward`` then just returns that scalar (its backward hands the
 stored dL/dcolor to the rasterizer's backward without another pass over the images) and ``compute_psnr`` the per-view

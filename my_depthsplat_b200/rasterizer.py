@@ -53,6 +53,20 @@ class ViewPack:
 
 
 @dataclass
+class RawScene:
+    """The Gaussians as the encoder head's raw output (gaussian_adapter.FusedAdapterDecoder): the adapter runs inside the
+    projection kernels.  head [B,Vc,37,H*W] and depth [B,Vc,H*W] are differentiable; image [B,Vc,3,H*W]; camera [B,Vc,56]."""
+    views: int
+    height: int
+    width: int
+    scale_min: float
+    scale_max: float
+    image: torch.Tensor
+    camera: torch.Tensor
+    cooked_out: Optional[torch.Tensor] = None   # tests: [B,N,40] world-space Gaussians as the kernel built them
+
+
+@dataclass
 class RenderStats:
     num_pairs: int = 0
     num_visible: int = 0
@@ -220,7 +234,18 @@ def release_scratch() -> None:
     _saved_pool.clear()
 
 
-def _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp: ViewPack):
+def _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp: ViewPack, raw: Optional[RawScene] = None):
+    if raw is not None:  # (means, covs) carry (head, depth)
+        head, depth = means, covs
+        B, N = head.shape[0], raw.views * raw.height * raw.width
+        sc = _lib.Scene()
+        sc.num_scenes, sc.num_gaussians, sc.sh_degree, sc.sh_coeffs = B, N, 2, 9
+        sc.cov_layout, sc.sh_layout = _lib.COV_3X3, _lib.SH_CHANNEL_MAJOR
+        sc.raw_head, sc.raw_depth, sc.raw_image, sc.raw_camera = _ptr(head), _ptr(depth), _ptr(raw.image), _ptr(raw.camera)
+        sc.raw_views, sc.raw_h, sc.raw_w = raw.views, raw.height, raw.width
+        sc.raw_scale_min, sc.raw_scale_max = float(raw.scale_min), float(raw.scale_max)
+        sc.raw_cooked_out = _ptr(raw.cooked_out)
+        return sc, _build_views(vp)
     B, N = means.shape[0], means.shape[1]
     sc = _lib.Scene()
     sc.num_scenes, sc.num_gaussians = B, N
@@ -233,22 +258,26 @@ def _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout,
     else:
         sc.sh_degree, sc.sh_coeffs, sc.sh_layout = 0, 1, _lib.SH_CHANNEL_MAJOR
         sc.harmonics, sc.colors_precomp = None, _ptr(colors)
+    return sc, _build_views(vp)
+
+
+def _build_views(vp: ViewPack):
     vw = _lib.Views()
     vw.num_views, vw.height, vw.width = vp.scene_index.shape[0], vp.height, vp.width
     vw.depth_mode = _DEPTH_MODES[vp.depth_mode]
     vw.scene_index, vw.viewmatrix, vw.projmatrix = _ptr(vp.scene_index), _ptr(vp.viewmatrix), _ptr(vp.projmatrix)
     vw.campos, vw.tanfov, vw.background = _ptr(vp.campos), _ptr(vp.tanfov), _ptr(vp.background)
     vw.scale, vw.depth_affine, vw.depth_clamp = _ptr(vp.scale), _ptr(vp.depth_affine), _ptr(vp.depth_clamp)
-    return sc, vw
+    return vw
 
 
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, covs, colors, opacities, means2d, vp: ViewPack, use_sh: bool, sh_degree: int, sh_layout: int,
-                want_radii: bool, count_work: bool):
+                want_radii: bool, count_work: bool, raw: Optional[RawScene] = None):
         # the library launches on the CURRENT device: make it the tensors' device for the duration of the call
         with torch.cuda.device(means.device):
-            return _Rasterize._forward(ctx, means, covs, colors, opacities, means2d, vp, use_sh, sh_degree, sh_layout, want_radii, count_work)
+            return _Rasterize._forward(ctx, means, covs, colors, opacities, means2d, vp, use_sh, sh_degree, sh_layout, want_radii, count_work, raw)
 
     @staticmethod
     def backward(ctx, g_color, g_depth, _g_radii, g_loss=None, _g_sse=None):
@@ -266,13 +295,14 @@ class _Rasterize(torch.autograd.Function):
 
     @staticmethod
     def _forward(ctx, means, covs, colors, opacities, means2d, vp: ViewPack, use_sh: bool, sh_degree: int, sh_layout: int,
-                 want_radii: bool, count_work: bool):
+                 want_radii: bool, count_work: bool, raw: Optional[RawScene] = None):
         L = _lib.load()
         dev = means.device
-        B, N = means.shape[0], means.shape[1]
+        B, N = (means.shape[0], means.shape[1]) if raw is None else (means.shape[0], raw.views * raw.height * raw.width)
+        ctx.raw = raw
         VV, H, W = vp.scene_index.shape[0], vp.height, vp.width
         stream = torch.cuda.current_stream(dev).cuda_stream
-        sc, vw = _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp)
+        sc, vw = _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp, raw)
 
         color = torch.empty((VV, 3, H, W), dtype=torch.float32, device=dev)
         depth = torch.empty((VV, H, W), dtype=torch.float32, device=dev) if vp.depth_mode is not None else None
@@ -388,9 +418,10 @@ class _Rasterize(torch.autograd.Function):
             pending.check(block=True)  # lazy mode: the forward's status word, normally long since written
         saved = lease.tensor
         dev = means.device
-        VV, N = vp.scene_index.shape[0], means.shape[1]
+        raw = ctx.raw
+        VV, N = vp.scene_index.shape[0], (means.shape[1] if raw is None else raw.views * raw.height * raw.width)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        sc, vw = _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp)
+        sc, vw = _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp, raw)
         g_color = (torch.zeros((VV, 3, vp.height, vp.width), dtype=torch.float32, device=dev) if g_color is None
                    else g_color.to(torch.float32).contiguous())
         if vp.depth_mode is not None:
@@ -408,6 +439,12 @@ class _Rasterize(torch.autograd.Function):
             _lib.check(L.b200s_backward(C.byref(sc), C.byref(vw), C.byref(plan), saved.data_ptr(), scratch.data_ptr(), C.byref(out),
                                         C.byref(gout), C.byref(gin), stream), "b200s_backward")
 
+        if raw is not None:
+            # raw scene: gradients w.r.t. the head's channel planes and the depth, straight out of the projection backward
+            d_head, d_depth = torch.empty_like(means), torch.empty_like(covs)
+            gin = _lib.GradIn(None, None, None, None, None, _ptr(d_m2d), 0, 0, 0, 0, 0, 0, _ptr(d_head), _ptr(d_depth))
+            call(gin)
+            return d_head, d_depth, None, None, d_m2d, None, None, None, None, None, None, None
         if reducer is not None and getattr(reducer, "scatter", False):
             # reduce-scatter by Gaussian range: outputs are views of a symmetric-memory buffer; the projection backward runs
             # in pieces that each cover a part of EVERY rank's range, and the reducer pulls this rank's share of a finished
@@ -453,7 +490,7 @@ class _Rasterize(torch.autograd.Function):
                     works += reducer.reduce_async(parts)
                 for w in works:
                     w.wait()
-        return d_means, d_covs, d_colors, d_op, d_m2d, None, None, None, None, None, None
+        return d_means, d_covs, d_colors, d_op, d_m2d, None, None, None, None, None, None, None
 
 
 def _grad_tensors(*like):
@@ -505,3 +542,20 @@ def rasterize(means: torch.Tensor, covariances: torch.Tensor, colors: torch.Tens
     if views.mse_target is not None:
         views.mse_result = (loss, sse)
     return color, (depth if views.depth_mode is not None else None), (radii if want_radii else None)
+
+
+def rasterize_raw(head: torch.Tensor, depth: torch.Tensor, raw: RawScene, views: ViewPack, *, want_radii: bool = False,
+                  count_work: bool = False):
+    """The encoder head's raw output rendered directly: head [B,Vc,37,H*W], depth [B,Vc,H*W] (both differentiable), the
+    rest in ``raw``.  Returns (color [VV,3,H,W], depth image [VV,H,W] | None, radii [VV,N] | None)."""
+    head = _f32c(head, "head"); depth = _f32c(depth, "depth")
+    raw.image = _f32c(raw.image, "image"); raw.camera = _f32c(raw.camera, "camera")
+    B = head.shape[0]
+    hw = raw.height * raw.width
+    if head.shape != (B, raw.views, 37, hw) or depth.shape != (B, raw.views, hw) or raw.image.shape != (B, raw.views, 3, hw) or raw.camera.shape != (B, raw.views, 56):
+        raise ValueError("raw scene tensors must be head [B,Vc,37,H*W], depth [B,Vc,H*W], image [B,Vc,3,H*W], camera [B,Vc,56]")
+    if hw % 256:
+        raise ValueError("the fused adapter needs H*W of the context views to be a multiple of 256")
+    dummy = head.new_empty(0)
+    color, dimg, radii, _, _ = _Rasterize.apply(head, depth, dummy, dummy, None, views, True, 2, _lib.SH_CHANNEL_MAJOR, want_radii, count_work, raw)
+    return color, (dimg if views.depth_mode is not None else None), (radii if want_radii else None)

@@ -37,7 +37,7 @@ def test_fused_loss_gradients_and_psnr(name, l1, scale):
     (ref * scale).backward()
 
     g1 = cuda_leaf_gaussians(sc)
-    fused = dec.forward(g1, *cams, mse_target=target, mse_weight=0.5, mse_l1=l1)
+    fused = dec.forward_fused_mse(g1, *cams, mse_target=target, mse_weight=0.5, mse_l1=l1)
     assert torch.equal(fused.color, plain.color)
     got = loss_fn.forward(fused, batch, g1, 0, l1_loss=l1)
     assert got is fused.fused_mse.loss
@@ -63,7 +63,7 @@ def test_fused_loss_next_to_a_loss_on_the_colour():
     g0, g1 = cuda_leaf_gaussians(sc), cuda_leaf_gaussians(sc)
     plain = dec.forward(g0, *cams)
     (((plain.color - target) ** 2).mean() + (plain.color * sc.grad_color).sum()).backward()
-    fused = dec.forward(g1, *cams, mse_target=target, mse_weight=1.0)
+    fused = dec.forward_fused_mse(g1, *cams, mse_target=target, mse_weight=1.0)
     (fused.fused_mse.loss + (fused.color * sc.grad_color).sum()).backward()
     for k in ("means", "covariances", "harmonics", "opacities"):
         a, b = getattr(g1, k).grad, getattr(g0, k).grad
