@@ -155,7 +155,9 @@ typedef struct B200sPlan {
 /* Device status block (first bytes of the saved workspace). */
 typedef struct B200sStatus {
   uint64_t num_pairs;     /* R: total (tile,Gaussian) pairs over all views of the call */
-  uint32_t overflow;      /* 1 if R > pair_capacity: nothing downstream of duplication ran */
+  uint32_t overflow;      /* nonzero: nothing downstream of stage A ran.  bit 0: R > pair_capacity (re-run with a larger capacity);
+                             bit 1 (BINNED mode): more than 2^26 pairs, most of them in bins too long for shared memory
+                             (re-run with a B200S_SORT_GLOBAL plan) */
   uint32_t num_visible;   /* Gaussian-view pairs that survived culling (Nv summed over views) */
   uint64_t tested;        /* optional flop accounting (filled when B200sOut.count_work != 0) */
   uint64_t blended;
@@ -170,7 +172,7 @@ typedef struct B200sOut {
   int32_t* radii;    /* [VV,N] or NULL */
   int32_t count_work;/* != 0: accumulate tested/blended/max_tile_len into the status block */
   void* status_host; /* optional: DEVICE-ACCESSIBLE pointer to 16 bytes of mapped pinned host memory (b200s_host_alloc).
-                        Stage A stores {u64 num_pairs, u32 overflow flag, u32 nonzero marker (BINNED: 0x80000000 |
+                        Stage A stores {u64 num_pairs, u32 overflow flags (B200sStatus.overflow), u32 nonzero marker (BINNED: 0x80000000 |
                         max_bin_len)} there directly from the kernel, so the host can read the pair count after an
                         event wait (or lazily, much later) without occupying a copy engine. */
   /* Optional loss-side fusion: the reference computes weight * mean((color - target)^2) (or the mean

@@ -60,6 +60,7 @@ cudaError_t launch_tile_ranges(const uint64_t* keys, CountRef cnt, uint2* ranges
 // entries a bin of the class holds in shared memory (8 B each next to 16 KB of bucket counters; 4 / 2 / 1 CTAs per SM)
 constexpr int BIN_CAP_XS = 4960, BIN_CAP_S = 12224, BIN_CAP_L = 26976;
 constexpr int BIN_CLASSES = 4;
+constexpr unsigned long long BIN_GLOBAL_MIN_PAIRS = 1ull << 26;  // below this the LSD path is fast enough whatever the bin lengths
 struct BinSortWork {
   uint32_t* class_list;   // [BIN_CLASSES][bins] bin ids per size class
   uint32_t* class_count;  // [BIN_CLASSES]

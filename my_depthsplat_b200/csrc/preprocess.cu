@@ -533,9 +533,10 @@ __global__ void __launch_bounds__(BSCAN_THREADS) bin_scan_kernel(const uint32_t*
   __shared__ unsigned long long s_wsum[BSCAN_THREADS / 32];
   __shared__ uint32_t s_cls[BIN_CLASSES];
   __shared__ uint32_t s_max;
+  __shared__ unsigned long long s_long;  // pairs in bins that only the global-memory LSD path takes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < BIN_CLASSES) s_cls[tid] = 0;
-  if (tid == 0) s_max = 0;
+  if (tid == 0) { s_max = 0; s_long = 0ull; }
   const int per = (bins + BSCAN_THREADS - 1) / BSCAN_THREADS;
   const int b0 = min(bins, tid * per), b1 = min(bins, b0 + per);
   unsigned long long tsum = 0;
@@ -561,12 +562,17 @@ __global__ void __launch_bounds__(BSCAN_THREADS) bin_scan_kernel(const uint32_t*
     if (c) {
       const int cls = c <= (uint32_t)BIN_CAP_XS ? 0 : (c <= (uint32_t)BIN_CAP_S ? 1 : (c <= (uint32_t)BIN_CAP_L ? 2 : 3));
       w.class_list[(size_t)cls * bins + atomicAdd(&s_cls[cls], 1u)] = (uint32_t)b;
+      if (cls == 3) atomicAdd(&s_long, (unsigned long long)c);
     }
   }
   __syncthreads();
   if (tid < BIN_CLASSES) { w.class_count[tid] = s_cls[tid]; w.class_next[tid] = 0; }
   if (tid == 0) {
-    const uint32_t over = total > pair_capacity ? 1u : 0u;
+    // flags: bit 0 = more pairs than the buffers hold; bit 1 = most of a LARGE pair count sits in bins that are too long for
+    // shared memory (stress scenes: every Gaussian covers hundreds of tiles) -- one CTA per 10^5..10^6-entry bin and one
+    // atomic per pair are the wrong tools there, the host re-runs the call in GLOBAL sort mode.  Either way nothing
+    // downstream runs (every later kernel returns when the word is nonzero).
+    const uint32_t over = (total > pair_capacity ? 1u : 0u) | ((total > BIN_GLOBAL_MIN_PAIRS && 2ull * s_long > total) ? 2u : 0u);
     status->num_pairs = total;
     status->overflow = over;
     status->max_bin_len = s_max;

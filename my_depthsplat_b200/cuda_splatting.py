@@ -198,8 +198,22 @@ def render_views(
                                   gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh,
                                   depth_mode, want_radii, count_work, grad_reducer, mse)
     except PairLimitExceeded:
-        if V == 1:
+        if V == 1 and B == 1:
             raise
+    if V == 1:  # one view per scene: split the SCENES instead
+        hb = B // 2
+        bsl = (slice(0, hb), slice(hb, B))
+        sub = [None if mse is None else dict(target=mse["target"][sl], weight=mse["weight"], l1=mse.get("l1", False), count=mse["count"]) for sl in bsl]
+        parts = [render_views(extrinsics[sl], intrinsics[sl], near[sl], far[sl], image_shape, background_color if background_color.dim() == 1 else background_color[sl],
+                              gaussian_means[sl], gaussian_covariances[sl], gaussian_sh_coefficients[sl], gaussian_opacities[sl], scale_invariant, use_sh,
+                              depth_mode, want_radii, count_work, grad_reducer, m) for sl, m in zip(bsl, sub)]
+        if mse is not None:
+            mse["loss"] = sub[0]["loss"] + sub[1]["loss"]
+            mse["sse_clipped"] = torch.cat([sub[0]["sse_clipped"], sub[1]["sse_clipped"]], dim=0)
+        out = [torch.cat([p[0] for p in parts], dim=0), None if parts[0][1] is None else torch.cat([p[1] for p in parts], dim=0)]
+        if want_radii:
+            out.append(torch.cat([p[2] for p in parts], dim=0))
+        return tuple(out)
     # more than 2^32 (tile, Gaussian) pairs in one call (huge Gaussians, many views): split the views and
     # concatenate -- each half is its own autograd node, gradients add up as usual
     half = V // 2

@@ -81,6 +81,7 @@ class RenderStats:
 # "global": one onesweep radix sort over 64-bit (view | tile | depth) keys.  Same lists and ranges, bit for bit.
 sort_mode = os.environ.get("B200S_SORT_MODE", "binned")
 _SORT_MODES = {"binned": _lib.SORT_BINNED, "global": _lib.SORT_GLOBAL}
+_mode_hint: dict = {}   # problem shapes whose bins turned out too long for the BINNED mode (stage A said so): GLOBAL from then on
 
 # "event" (default): the host waits for stage A of every forward (pair count known, overflow repaired transparently);
 # "lazy": no host wait once a problem shape has been seen twice (see _Rasterize.forward)
@@ -124,6 +125,8 @@ class _Pending:
             raise RuntimeError("stage A did not report its pair count (status word not written)")
         _note_pairs(self.key, num_pairs)
         last_stats.num_pairs = num_pairs
+        if flags & 2:
+            _mode_hint[self.key] = _lib.SORT_GLOBAL
         if flags & 0xFFFFFFFF:
             _seen[self.key] = 0  # back to the waiting protocol until the shape has settled again
             raise PairCapacityOverflow(
@@ -149,7 +152,17 @@ _PAIR_LIMIT = (1 << 32) - 8193  # list positions are 32-bit
 
 
 class PairLimitExceeded(RuntimeError):
-    """One call would produce 2^32 or more (tile, Gaussian) pairs; render fewer views per call."""
+    """One call would produce 2^32 or more (tile, Gaussian) pairs -- or need more workspace than ``max_workspace_bytes`` --;
+    render fewer views per call (cuda_splatting.render_views splits the views and retries on its own)."""
+
+
+# Bound on the two workspaces of ONE call (bytes).  The pair buffers take 24 bytes per (tile, Gaussian) pair; a stress scene
+# (BASELINE config 5: 3 M Gaussians with scales up to 0.5, 1.3 * 10^9 pairs per 512x960 view) would otherwise take whatever
+# the pair count asks for (110 GB for two views in round 1).  A call whose MEASURED pair count needs more than this and has
+# more than one view raises PairLimitExceeded, so that the views are rendered in smaller groups; a single view is always
+# rendered, whatever it needs.
+max_workspace_bytes = int(float(os.environ.get("B200S_MAX_WORKSPACE_GB", "40")) * 1e9)
+_BYTES_PER_PAIR = 24
 
 
 class _HostStatusRing:
@@ -336,10 +349,12 @@ class _Rasterize(torch.autograd.Function):
         else:
             cap = _capacity_hint.get(key) or max(4 * N * VV, 1 << 16)
             cap = min(cap, _PAIR_LIMIT)
+            if VV > 1:  # the first, speculative attempt stays inside the budget too
+                cap = max(min(cap, (max_workspace_bytes - VV * (N * 72 + H * W * 8)) // _BYTES_PER_PAIR), 1 << 16)
         words = _status_ring.words
         retries = 0
         while True:
-            plan = _lib.plan(B, N, VV, H, W, cap, _SORT_MODES[sort_mode])
+            plan = _lib.plan(B, N, VV, H, W, cap, _mode_hint.get(key, _SORT_MODES[sort_mode]))
             lease = _SavedLease(dev, plan.saved_bytes)
             saved = lease.tensor
             scratch = _scratch(dev, plan.scratch_bytes)
@@ -367,9 +382,16 @@ class _Rasterize(torch.autograd.Function):
                 break
             words[2 * slot] = 0
             words[2 * slot + 1] = 0
+            if overflow & 2:  # bins too long for the BINNED mode: this shape renders in GLOBAL mode from now on
+                _mode_hint[key] = _lib.SORT_GLOBAL
             if num_pairs >= _PAIR_LIMIT:
                 raise PairLimitExceeded(f"{num_pairs} (tile, Gaussian) pairs in one call exceed the 2^32 limit; render fewer views per call")
+            if VV > 1 and num_pairs * _BYTES_PER_PAIR + VV * (N * 72 + H * W * 8) > max_workspace_bytes:
+                raise PairLimitExceeded(f"{num_pairs} (tile, Gaussian) pairs for {VV} views need {num_pairs * _BYTES_PER_PAIR / 1e9:.1f} GB of pair buffers, "
+                                        f"more than max_workspace_bytes = {max_workspace_bytes / 1e9:.0f} GB; render fewer views per call")
             cap = min(int(num_pairs * 1.25) + 4096, _PAIR_LIMIT)
+            if VV > 1:
+                cap = min(cap, max((max_workspace_bytes - VV * (N * 72 + H * W * 8)) // _BYTES_PER_PAIR, num_pairs))
             retries += 1
         if not lazy:
             _note_pairs(key, num_pairs)

@@ -157,6 +157,36 @@ def test_huge_footprints_split_views_and_stay_correct():
     assert R.last_stats.num_pairs > 10 * gc.means.shape[1]  # most Gaussians cover a large part of the 24-tile image
 
 
+def test_workspace_budget_splits_the_views_and_changes_nothing():
+    """rasterizer.max_workspace_bytes bounds the workspaces of one call: a call whose measured pair count needs more is split
+    into smaller groups of views (and of scenes, when every scene has one view) -- same images, same gradients."""
+    from my_depthsplat_b200 import rasterizer as R
+    scene = make_scene("small_stress", batch=2, v_tgt=2)
+    g0, g1 = _cuda(scene.gaussians), _cuda(scene.gaussians)
+    for g in (g0, g1):
+        for t in (g.means, g.covariances, g.harmonics, g.opacities):
+            t.requires_grad_()
+    ref, _ = _render(scene, g0)
+    (ref * scene.grad_color.cuda()).sum().backward()
+    pairs = R.last_stats.num_pairs
+    old = R.max_workspace_bytes
+    R._capacity_hint.clear()
+    N = g0.means.shape[1]
+    H, W = scene.image_shape
+    # room for the records of all four views but for the pairs of about one
+    R.max_workspace_bytes = 4 * (N * 72 + H * W * 8) + (pairs // 3) * 24
+    try:
+        got, _ = _render(scene, g1)
+        assert R.last_stats.num_pairs < pairs           # the last call rendered a subset of the views
+        (got * scene.grad_color.cuda()).sum().backward()
+    finally:
+        R.max_workspace_bytes = old
+        R._capacity_hint.clear()
+    assert torch.equal(got, ref)
+    for a, b in ((g1.means, g0.means), (g1.covariances, g0.covariances), (g1.harmonics, g0.harmonics), (g1.opacities, g0.opacities)):
+        torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-6 * float(b.grad.abs().max()))
+
+
 def test_camera_block_graph_replays_the_eager_sequence_bit_for_bit():
     """The ~60 torch kernels of the camera block are captured once per (device, views, flags) in a CUDA graph
     (cuda_splatting._camera_tensors_cached): same outputs as the eager sequence for every new set of cameras, and a
