@@ -431,8 +431,8 @@ def run_ours(args):
     if tpath.exists() and args.config == "C2T" and V == cfg.v_tgt:
         tj = json.loads(tpath.read_text())
         traffic = {k: v["dram_bytes_per_launch"] for k, v in tj.items() if isinstance(v, dict)}
-        if "sort_passes" in traffic:
-            traffic["sort_passes"] *= plan.sort_passes  # the stage is all passes
+        if "sort_passes" in traffic and not binned and "kernels" not in tj["sort_passes"]:
+            traffic["sort_passes"] *= plan.sort_passes  # round-1 file: one pass captured; the stage is all passes
     dom = max(stage_report, key=lambda k: stage_report[k]["ms"]) if stage_report else None
     roofline = None
     if dom:
