@@ -304,10 +304,14 @@ __global__ void __launch_bounds__(T, MIN_CTAS) bucket_sort_kernel(const BinSortA
     if ((tid & 31) == 0) { atomicMin(&s_mm[0], kmn); atomicMax(&s_mm[1], kmx); }
     __syncthreads();
     const uint32_t kmin = s_mm[0];
-    const int kbits = 32 - __clz(s_mm[1] - kmin);
-    const int low = kbits > bbits ? kbits - bbits : 0;
+    // bucket(k) = floor((k - min) * nb / (range + 1)): monotone, and ALL nb buckets span [min, max] (a shift by whole bits
+    // would leave up to half of them unused); evaluated as the high word of a 32 x 32 bit product
+    const uint32_t krange = s_mm[1] - kmin;
+    const uint32_t mul = (uint32_t)min(0xffffffffull, ((unsigned long long)nb << 32) / ((unsigned long long)krange + 1ull));
+    const bool exact = krange < (uint32_t)nb;  // fewer distinct depths than buckets: one depth value per bucket
+#define BUCKET(k) (exact ? ((k) - kmin) : __umulhi((k) - kmin, mul))
     for (uint32_t i = tid; i < n; i += T) {
-      const uint32_t b = (src[i].x - kmin) >> low;
+      const uint32_t b = BUCKET(src[i].x);
       atomicAdd(&hist[b >> 1], 1u << ((b & 1u) * 16));
     }
     __syncthreads();
@@ -315,14 +319,14 @@ __global__ void __launch_bounds__(T, MIN_CTAS) bucket_sort_kernel(const BinSortA
     __syncthreads();
     for (uint32_t i = tid; i < n; i += T) {
       const uint2 e = src[i];
-      const uint32_t b = (e.x - kmin) >> low, sh = (b & 1u) * 16;
+      const uint32_t b = BUCKET(e.x), sh = (b & 1u) * 16;
       const uint32_t pos = (atomicAdd(&hist[b >> 1], 1u << sh) >> sh) & 0xffffu;
       kB[pos] = e.x; vB[pos] = e.y;
     }
     __syncthreads();
     {  // more than RUN_CAP entries in one bucket?
       bool crowded = false;
-      for (uint32_t i = tid; i + RUN_CAP < n; i += T) crowded |= ((kB[i] - kmin) >> low) == ((kB[i + RUN_CAP] - kmin) >> low);
+      for (uint32_t i = tid; i + RUN_CAP < n; i += T) crowded |= BUCKET(kB[i]) == BUCKET(kB[i + RUN_CAP]);
       if (crowded) s_flag = 1;
     }
     __syncthreads();
@@ -333,17 +337,18 @@ __global__ void __launch_bounds__(T, MIN_CTAS) bucket_sort_kernel(const BinSortA
     uint32_t* __restrict__ out = a.vals_out + range.x;
     for (uint32_t i = tid; i < n; i += T) {
       const uint32_t k = kB[i], v = vB[i];
-      const uint32_t top = (k - kmin) >> low;
+      const uint32_t top = BUCKET(k);
       uint32_t pos = i;
-      const bool eq_prev = i > 0 && ((kB[i - 1] - kmin) >> low) == top, eq_next = i + 1 < n && ((kB[i + 1] - kmin) >> low) == top;
+      const bool eq_prev = i > 0 && BUCKET(kB[i - 1]) == top, eq_next = i + 1 < n && BUCKET(kB[i + 1]) == top;
       if (eq_prev || eq_next) {  // its place inside the bucket = the number of smaller (depth, index) pairs there
         uint32_t s = i, t = i + 1, smaller = 0;
-        while (s > 0) { const uint32_t ok = kB[s - 1]; if (((ok - kmin) >> low) != top) break; s--; smaller += ok < k || (ok == k && vB[s] < v); }
-        while (t < n) { const uint32_t ok = kB[t]; if (((ok - kmin) >> low) != top) break; smaller += ok < k || (ok == k && vB[t] < v); t++; }
+        while (s > 0) { const uint32_t ok = kB[s - 1]; if (BUCKET(ok) != top) break; s--; smaller += ok < k || (ok == k && vB[s] < v); }
+        while (t < n) { const uint32_t ok = kB[t]; if (BUCKET(ok) != top) break; smaller += ok < k || (ok == k && vB[t] < v); t++; }
         pos = s + smaller;
       }
       out[pos] = v;
     }
+#undef BUCKET
   }
 }
 

@@ -444,6 +444,11 @@ cudaError_t launch_composite_bwd(const CompArgs& a, int tiles, int views, bool d
   count_launches(1);
   // Two CTAs of four warps per tile, seven per SM (72 registers, 28 KB of shared memory: 28 warps per SM)
   dim3 g2(tiles * 2, views);
+  if (g_sort_knobs[2].load(std::memory_order_relaxed) == 8) {  // A/B: eight CTAs per SM at 64 registers
+    if (depth) composite_bwd_kernel<true, 4, 8><<<g2, 128, 0, stream>>>(a);
+    else composite_bwd_kernel<false, 4, 8><<<g2, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+  }
   if (depth) composite_bwd_kernel<true, 4, 7><<<g2, 128, 0, stream>>>(a);
   else composite_bwd_kernel<false, 4, 7><<<g2, 128, 0, stream>>>(a);
   return cudaGetLastError();

@@ -273,13 +273,22 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
             // conservative half-extents of the region where alpha can reach 1/255
             float ex = -1e30f, ey = -1e30f;  // never reaches alpha >= 1/255: fails every sub-tile test
             const float o255 = 255.0f * opac;
+            const float cA = __fmul_rn(q.c, det_inv), cB = __fmul_rn(-q.b, det_inv), cC = __fmul_rn(q.a, det_inv);
             if (o255 >= 1.0f) {
+              // bounding box of {A dx^2 + 2 B dx dy + C dy^2 <= tau2} for the STORED conic -- the numbers the blend evaluates
+              // (for elongated footprints det cancels, and the float conic is no longer the inverse of the float cov2D to
+              // within the margin); a conic that is not positive definite in floats is never culled
               const float tau2 = 2.0f * logf(o255);
-              ex = sqrtf(tau2 * q.a) * 1.01f + 0.1f;
-              ey = sqrtf(tau2 * q.c) * 1.01f + 0.1f;
+              const float dd = cA * cC - cB * cB;
+              if (dd > 0.f && cA > 0.f && cC > 0.f) {
+                ex = sqrtf(tau2 * cC / dd) * 1.01f + 0.1f;
+                ey = sqrtf(tau2 * cA / dd) * 1.01f + 0.1f;
+              } else {
+                ex = 1e30f; ey = 1e30f;
+              }
             }
             out.q0 = make_float4(px, py, ex, ey);
-            out.q1 = make_float4(__fmul_rn(q.c, det_inv), __fmul_rn(-q.b, det_inv), __fmul_rn(q.a, det_inv), opac);
+            out.q1 = make_float4(cA, cB, cC, opac);
             out.q2 = make_float4(rgb[0], rgb[1], rgb[2], zc);
             const uint32_t rect = (uint32_t)rx0 | ((uint32_t)ry0 << 8) | ((uint32_t)rx1 << 16) | ((uint32_t)ry1 << 24);
             out.q3 = make_float4(depth, __int_as_float(radius), __uint_as_float(rect), __uint_as_float(flags));

@@ -191,6 +191,11 @@ def render_views(
     B, V = extrinsics.shape[:2]
     h, w = image_shape
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (extrinsics, intrinsics, near, far)):
+        # the extension the reference binds has no camera gradients either, but its depth pass differentiates z through
+        # extrinsics.inverse() in PyTorch (cuda_splatting.py:238-241); here z is computed in-kernel
+        import warnings
+        warnings.warn("render_views: cameras / near / far that require grad get no gradient from the rasterizer", stacklevel=2)
     if mse is not None and "count" not in mse:
         mse["count"] = B * V * 3 * h * w
     try:
