@@ -53,7 +53,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -76,7 +76,7 @@ class ClockSampler:
         """Median SM clock and throttle reasons seen between wall-clock t0 and t1 (+- one sample period)."""
         self.f.flush()
         rows = self._rows()
-        sel = [r for r in rows if t0 - 0.25 <= r[0] <= t1 + 0.25] or rows[-3:]
+        sel = [r for r in rows if t0 - 0.1 <= r[0] <= t1 + 0.1] or rows[-3:]
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(sel)}
         reasons = set()
         sm = sorted(r[1] for r in sel)
@@ -246,6 +246,8 @@ def run_ours(args):
     sharded = decoder if (by_scene or by_range) else ViewShardedDecoder(
         decoder, fused_reduce=(world > 1 and args.fused_reduce), overlap_reduce=(world > 1 and args.overlap_reduce),
         nvls_reduce=(world > 1 and args.nvls_reduce), scatter_grads=scatter, pieces=args.pieces)
+    if scatter and not (getattr(sharded, "reducer", None) is not None and sharded.reducer.available):
+        scatter = False  # no NVLS multicast on this fabric: ViewShardedDecoder falls back to the NCCL all-reduce
     if getattr(sharded, "reducer", None) is not None and hasattr(sharded.reducer, "chunks") and os.environ.get("B200S_REDUCE_CHUNKS"):
         sharded.reducer.chunks = int(os.environ["B200S_REDUCE_CHUNKS"])
     gnames = ("means", "covariances", "harmonics", "opacities")

@@ -212,12 +212,12 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(const CompArgs 
 //
 // Per-pixel state of the reverse walk.  The reference recurrence keeps, per channel, the colour accumulated BEHIND the
 // current entry (accum = last_alpha * last_colour + (1 - last_alpha) * accum) and contracts it with dL/dpixel; the
-// contraction commutes with the recurrence, so only its scalar image is carried:
-//   E = sum_ch accum[ch] * dpix[ch]   ->   E' = last_alpha * D_last + (1 - last_alpha) * E,   D = sum_ch colour[ch] * dpix[ch]
+// contraction commutes with the recurrence, so only its scalar image is carried, advanced right after each entry:
+//   E = sum_ch accum[ch] * dpix[ch]   ->   E' = alpha * D + (1 - alpha) * E,   D = sum_ch colour[ch] * dpix[ch]
 template <bool DEPTH>
 struct PixState {
-  float T, tb, last_alpha;   // tb = final_T * sum_ch bg[ch] * dpix[ch]
-  float E, D_last;
+  float T, tb;               // tb = final_T * sum_ch bg[ch] * dpix[ch]
+  float E;
   float dpix[DEPTH ? 4 : 3];
   uint32_t last_contributor;
 };
@@ -255,11 +255,11 @@ __device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, PixStat
   D = fmaf(h2.y, s.dpix[1], D);
   D = fmaf(h2.z, s.dpix[2], D);
   if (DEPTH) D = fmaf(h2.w, s.dpix[3], D);
-  const float E = s.last_alpha * s.D_last + (1.f - s.last_alpha) * s.E;
-  s.E = live ? E : s.E;
-  s.D_last = live ? D : s.D_last;
-  s.last_alpha = live ? alpha : s.last_alpha;
-  const float dL_dalpha = (D - E) * s.T - s.tb * inv;
+  // E = the colour accumulated BEHIND this entry, contracted with dL/dpixel: after the entry it becomes alpha D + (1 - alpha) E,
+  // which leaves it untouched for alpha = 0 -- no selects, and the difference D - E serves both lines
+  const float dE = D - s.E;
+  const float dL_dalpha = dE * s.T - s.tb * inv;
+  s.E = fmaf(a_eff, dE, s.E);
   // q = G * dL/dalpha; the per-Gaussian factors (opacity, conic, half extent of the image, -1/2) are applied once per
   // (view, Gaussian) by the projection backward:
   //   dL/dmean2D = opacity * half * (-A*S_x - B*S_y, -C*S_y - B*S_x),  dL/dconic = -opacity/2 * (S_xx, S_xy, S_yy),
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel
   PixState<DEPTH> s;
   s.T = g.inside ? a.final_T[(size_t)view * HW + pid] : 0.f;
   s.last_contributor = g.inside ? a.n_contrib[(size_t)view * HW + pid] : 0u;
-  s.last_alpha = 0.f; s.E = 0.f; s.D_last = 0.f;
+  s.E = 0.f;
   float bg_dot = 0.f;
 #pragma unroll
   for (int ch = 0; ch < (DEPTH ? 4 : 3); ch++) s.dpix[ch] = 0.f;
@@ -442,13 +442,9 @@ cudaError_t launch_composite_bwd(const CompArgs& a, int tiles, int views, bool d
   dim3 grid(tiles, views);
   stage_mark(B200S_STAGE_COMP_BWD, stream);
   count_launches(1);
-  // Two CTAs of four warps per tile, seven per SM (72 registers, 28 KB of shared memory: 28 warps per SM)
+  // Two CTAs of four warps per tile, seven per SM (72 registers, 28 KB of shared memory: 28 warps per SM; eight per SM at
+  // 64 registers measured the same: 1.92 against 1.90 ms)
   dim3 g2(tiles * 2, views);
-  if (g_sort_knobs[2].load(std::memory_order_relaxed) == 8) {  // A/B: eight CTAs per SM at 64 registers
-    if (depth) composite_bwd_kernel<true, 4, 8><<<g2, 128, 0, stream>>>(a);
-    else composite_bwd_kernel<false, 4, 8><<<g2, 128, 0, stream>>>(a);
-    return cudaGetLastError();
-  }
   if (depth) composite_bwd_kernel<true, 4, 7><<<g2, 128, 0, stream>>>(a);
   else composite_bwd_kernel<false, 4, 7><<<g2, 128, 0, stream>>>(a);
   return cudaGetLastError();

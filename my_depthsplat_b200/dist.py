@@ -327,7 +327,18 @@ class RangeScatterReducer:
         self._outs = {}
         self._turn = 0
         self._side = None
-        self.available = self.world > 1 and torch.cuda.is_available()
+        self.available = self.world > 1 and torch.cuda.is_available() and self._probe()
+
+    def _probe(self) -> bool:
+        """Symmetric memory with an NVLS multicast mapping on this fabric?  (Collective: every rank constructs the reducer
+        at the same point.)  Without it the callers fall back to NCCL."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(1024, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+            h = symm_mem.rendezvous(t, self.group)
+            return bool(h.multicast_ptr)
+        except Exception:
+            return False
 
     def begin(self, shapes, device):
         import torch.distributed._symmetric_memory as symm_mem

@@ -24,7 +24,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
-from .dist import all_gather_views, shard_bounds
+from .dist import _require_views, all_gather_views, shard_bounds
 from .types import DecoderOutput, Gaussians
 
 
@@ -44,6 +44,7 @@ def render_clip(decoder, gaussians: Gaussians, extrinsics: Tensor, intrinsics: T
     world, rank = _world(group)
     B, V = extrinsics.shape[:2]
     H, W = image_shape
+    _require_views(V, world)  # a rank without frames would skip the gather and hang the others
     lo, hi = shard_bounds(V, world, rank)
     v = hi - lo
     dev = extrinsics.device

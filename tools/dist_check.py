@@ -62,8 +62,17 @@ def range_grads(dec):
 rk_dec = RangeShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), pieces=3)
 rk = [range_grads(rk_dec) for _ in range(4)]   # four calls: the symmetric buffers rotate
 rn = range_grads(RangeShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), kernel_reduce=False))
+# (f) replicated Gaussians, gradients reduce-scattered: the own range holds the sum over all ranks, the rest is zero
+sc_dec = ViewShardedDecoder(get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), cfg).to(dev), scatter_grads=True, pieces=3)
+sg = [[t.clone() for t in grads(sc_dec, (lo, hi))] for _ in range(4)]
 torch.cuda.synchronize()
 ok = True
+for k, nm in enumerate(("means", "covariances", "harmonics", "opacities")):
+    scale = float(single[k].abs().max())
+    inside = max(float((sg[j][k][:, glo:ghi] - single[k][:, glo:ghi]).abs().max()) / scale for j in range(4)) if ghi > glo else 0.0
+    outside = max(float(sg[j][k][:, :glo].abs().max() if glo else 0.0) + float(sg[j][k][:, ghi:].abs().max() if ghi < N else 0.0) for j in range(4))
+    print(f"rank {rank} {nm:12s} scatter_grads: |own range - single| {inside:.2e}, largest value outside the range {outside:.1e} (4 calls)", flush=True)
+    ok &= inside < 2e-4 and outside == 0.0
 for k, nm in enumerate(("means", "covariances", "harmonics", "opacities")):
     ref = single[k][:, glo:ghi]
     scale = float(single[k].abs().max())
