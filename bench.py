@@ -207,7 +207,9 @@ def run_ours(args):
         bs, vs = slice(rank * args.scenes, (rank + 1) * args.scenes), slice(None)
     else:
         scene_cpu = make_scene(cfg, v_tgt=V * world)  # same seed on every rank -> identical (replicated) Gaussians
-        bs, vs = slice(None), slice(rank * V, (rank + 1) * V)  # this rank's shard of the target views
+        # this rank's shard of the target views: interleaved (rank, rank + N, ...) by default, so that every rank's views span the
+        # whole camera path like the N = 1 run's do; --contiguous-views gives each rank one stretch of the path
+        bs, vs = slice(None), (slice(rank * V, (rank + 1) * V) if args.contiguous_views else slice(rank, None, world))
     H, W = scene_cpu.image_shape
     N = scene_cpu.gaussians.means.shape[1]
     g_ = scene_cpu.gaussians
@@ -241,11 +243,11 @@ def run_ours(args):
     decoder = get_decoder(DecoderSplattingCUDACfg(name="splatting_cuda"), dataset_cfg).to(dev)
     # view sharding + ONE NCCL all-reduce of the flattened per-Gaussian gradients in the backward (identity at N=1)
     full_dev = {k: getattr(g_, k)[bs].to(dev) for k in ("means", "covariances", "harmonics", "opacities")} if by_range else devt
-    ranged = RangeShardedDecoder(decoder, pieces=args.pieces, kernel_reduce=not args.nccl_scatter) if (by_range or e2e_ranges) else None
+    ranged = RangeShardedDecoder(decoder, pieces=args.pieces, kernel_reduce=not args.nccl_scatter, interleave=not args.contiguous_views) if (by_range or e2e_ranges) else None
     scatter = world > 1 and args.grads == "scatter" and not (args.fused_reduce or args.overlap_reduce or args.nvls_reduce)
     sharded = decoder if (by_scene or by_range) else ViewShardedDecoder(
         decoder, fused_reduce=(world > 1 and args.fused_reduce), overlap_reduce=(world > 1 and args.overlap_reduce),
-        nvls_reduce=(world > 1 and args.nvls_reduce), scatter_grads=scatter, pieces=args.pieces)
+        nvls_reduce=(world > 1 and args.nvls_reduce), scatter_grads=scatter, pieces=args.pieces, interleave=not args.contiguous_views)
     if scatter and not (getattr(sharded, "reducer", None) is not None and sharded.reducer.available):
         scatter = False  # no NVLS multicast on this fabric: ViewShardedDecoder falls back to the NCCL all-reduce
     if getattr(sharded, "reducer", None) is not None and hasattr(sharded.reducer, "chunks") and os.environ.get("B200S_REDUCE_CHUNKS"):
@@ -391,7 +393,7 @@ def run_ours(args):
     # ---- work counters of one forward (pairs, visible, tested, blended) --------------------------------
     from my_depthsplat_b200.cuda_splatting import render_views
     with torch.no_grad():
-        render_views(*((devt[k] if by_scene else shard_views(devt[k], world, rank)) for k in ("extrinsics", "intrinsics", "near", "far")), (H, W), decoder.background_color,
+        render_views(*((devt[k] if by_scene else shard_views(devt[k], world, rank, interleave=not args.contiguous_views)) for k in ("extrinsics", "intrinsics", "near", "far")), (H, W), decoder.background_color,
                      full_dev["means"], full_dev["covariances"], full_dev["harmonics"], full_dev["opacities"], count_work=True)
     st = R.last_stats
     plan = _lib.plan(B_local, N, B_local * V, H, W, max(st.num_pairs, 1), R._SORT_MODES[R.sort_mode])
@@ -498,7 +500,7 @@ def run_ours(args):
                        "parallelism": (f"scene-sharded x{world}: {B_local} scene(s) per GPU, no collective on the rendering path") if by_scene else
                        (f"view-sharded x{world}, Gaussians sharded by range ({N // world} per rank): NCCL all-gather over NVLink in the forward, "
                         + ("NCCL reduce-scatter" if args.nccl_scatter else f"reduce-scatter by the library's NVLS kernel (multimem.ld_reduce) in {args.pieces} pieces under the projection backward")
-                        + " of the per-Gaussian gradients in the backward") if by_range else f"view-sharded x{world}, Gaussians replicated" + (f", per-Gaussian gradients reduce-scattered by Gaussian range (library NVLS kernel, {args.pieces} pieces under the projection backward)" if scatter else "") + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
+                        + " of the per-Gaussian gradients in the backward") if by_range else f"view-sharded x{world} ({'contiguous' if args.contiguous_views else 'interleaved'} views), Gaussians replicated" + (f", per-Gaussian gradients reduce-scattered by Gaussian range (library NVLS kernel, {args.pieces} pieces under the projection backward)" if scatter else "") + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
                                         else ("" if scatter else ", NCCL all-reduce of per-Gaussian grads" + (" in 2 chunks overlapped with the projection backward" if args.overlap_reduce else ""))) if world > 1 else "")},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_step_e, 4), "pinned_copy_bandwidth": pcie, "allocator_events": alloc_events,
@@ -530,6 +532,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2T")
     ap.add_argument("--views", type=int, default=0, help="target views per GPU (default: the config's)")
+    ap.add_argument("--contiguous-views", action="store_true", help="N>1: every rank renders one contiguous stretch of the target views (default: interleaved)")
     ap.add_argument("--e2e-replicated", action="store_true", help="N>1: the e2e leg copies the full replicated Gaussians per rank (round-1 layout)")
     ap.add_argument("--grads", default="scatter", choices=["allreduce", "scatter"],
                     help="N>1, --shard views: all-reduce of the per-Gaussian gradients (every rank gets all of them), or reduce-scatter "

@@ -48,8 +48,13 @@ def _require_views(num_views: int, world_size: int) -> None:
                          "(use a smaller process group for this call, or shard scenes instead)")
 
 
-def shard_views(t: Tensor, world_size: int, rank: int, dim: int = 1) -> Tensor:
-    """Slice of a ``[B, V, ...]`` camera tensor that belongs to ``rank``."""
+def shard_views(t: Tensor, world_size: int, rank: int, dim: int = 1, interleave: bool = False) -> Tensor:
+    """The views of a ``[B, V, ...]`` camera tensor that belong to ``rank``: a contiguous slice, or -- ``interleave`` -- the
+    views rank, rank + world, rank + 2 world, ...  Along a camera path neighbouring views cost about the same, so
+    contiguous slices give every rank a different part of the path (and a different load); interleaved, every rank's
+    views span the whole path."""
+    if interleave:
+        return t[(slice(None),) * dim + (slice(rank, None, world_size),)]
     a, b = shard_bounds(t.shape[dim], world_size, rank)
     return t.narrow(dim, a, b - a)
 
@@ -248,11 +253,14 @@ class ViewShardedDecoder(torch.nn.Module):
 
     def __init__(self, decoder: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, gather: bool = False,
                  fused_reduce: bool = False, overlap_reduce: bool = False, nvls_reduce: bool = False, scatter_grads: bool = False,
-                 pieces: int = 4):
+                 pieces: int = 4, interleave: bool = False):
         super().__init__()
         self.decoder = decoder
         self.group = group
         self.gather = gather
+        self.interleave = interleave  # rank r renders views r, r + world, ... instead of a contiguous slice (training only)
+        if interleave and gather:
+            raise ValueError("gather=True reassembles contiguous slices; use interleave for training (local views only)")
         # scatter_grads: REDUCE-SCATTER instead of all-reduce -- every rank gets the summed gradient of its own Gaussian range
         # (range_bounds) and zeros elsewhere, pulled out of the NVSwitch in pieces under the projection backward
         if scatter_grads and dist.is_initialized() and dist.get_world_size(group) > 1 and hasattr(decoder, "grad_reducer"):
@@ -281,7 +289,7 @@ class ViewShardedDecoder(torch.nn.Module):
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         V = extrinsics.shape[1]
         _require_views(V, world)
-        sl = [shard_views(t, world, rank) for t in (extrinsics, intrinsics, near, far)]
+        sl = [shard_views(t, world, rank, interleave=self.interleave) for t in (extrinsics, intrinsics, near, far)]
         fused = self.reducer is not None and self.reducer.available
         g = sync_gaussian_grads(gaussians, self.group) if (torch.is_grad_enabled() and not fused) else gaussians
         out = self.decoder.forward(g, *sl, image_shape, depth_mode=depth_mode)
@@ -489,10 +497,12 @@ class RangeShardedDecoder(torch.nn.Module):
     contiguous slice of the views from the all-gathered Gaussians and gets back the gradient of its own range, summed
     over all ranks' views.  ``num_gaussians`` is N, the Gaussians per scene over all ranks."""
 
-    def __init__(self, decoder: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, pieces: int = 4, kernel_reduce: bool = True):
+    def __init__(self, decoder: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, pieces: int = 4, kernel_reduce: bool = True,
+                 interleave: bool = False):
         super().__init__()
         self.decoder = decoder
         self.group = group
+        self.interleave = interleave
         self.reducer = None
         if kernel_reduce and dist.is_initialized() and dist.get_world_size(group) > 1 and torch.cuda.is_available() and hasattr(decoder, "grad_reducer"):
             self.reducer = RangeScatterReducer(group, pieces)
@@ -510,7 +520,7 @@ class RangeShardedDecoder(torch.nn.Module):
         if hasattr(self.decoder, "grad_reducer"):
             self.decoder.grad_reducer = self.reducer if by_kernel else None
         m, c, h, o = _GatherRanges.apply(self.group, num_gaussians, by_kernel, local.means, local.covariances, local.harmonics, local.opacities)
-        sl = [shard_views(t, world, rank) for t in (extrinsics, intrinsics, near, far)]
+        sl = [shard_views(t, world, rank, interleave=self.interleave) for t in (extrinsics, intrinsics, near, far)]
         return self.decoder.forward(Gaussians(m, c, h, o), *sl, image_shape, depth_mode=depth_mode)
 
 
