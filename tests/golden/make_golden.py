@@ -11,8 +11,11 @@ oracle's stage outputs (sorted keys, values, tile ranges) of every view.
 The GPU box has no /root/reference: the fixtures are how the reference's glue travels there.
 """
 import hashlib
+import os
 import sys
 from pathlib import Path
+
+os.environ.setdefault("MKL_CBWR", "COMPATIBLE")   # host-independent MKL code path (see tests/conftest.py)
 
 import numpy as np
 import torch
@@ -21,7 +24,7 @@ HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parents[1]))
 sys.path.insert(0, str(HERE.parent))
 
-from helpers import leaf_gaussians, load_reference_cuda_splatting, per_view_extension_inputs  # noqa: E402
+from helpers import input_digest, leaf_gaussians, load_reference_cuda_splatting, per_view_extension_inputs  # noqa: E402
 from my_depthsplat_b200.scenes import make_scene  # noqa: E402
 from test_reference_glue import _ref_render  # noqa: E402
 
@@ -56,7 +59,7 @@ def main():
         loss.backward()
         arrays = dict(color=color.detach().numpy(), d_means=g.means.grad.numpy(), d_covariances=g.covariances.grad.numpy(),
                       d_harmonics=g.harmonics.grad.numpy(), d_opacities=g.opacities.grad.numpy(),
-                      stage_digests=np.array(stage_digests(scene)))
+                      stage_digests=np.array(stage_digests(scene)), input_digest=np.array(input_digest(scene)))
         if depth is not None:
             arrays["depth"] = depth.detach().numpy()
         path = HERE / f"{name}_{depth_mode or 'color'}.npz"

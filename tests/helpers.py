@@ -70,6 +70,23 @@ def per_view_extension_inputs(scene, b: int, v: int, scale_invariant: bool = Tru
     )
 
 
+def input_digest(scene) -> str:
+    """sha256 over everything the oracle is fed for `scene` (Gaussians, upstream gradients, per-view extension
+    arguments).  Scene generation and camera glue use host BLAS; a fixture records the digest of the inputs it was made
+    from so that a test can tell "the oracle drifted" from "this host builds the inputs with different last bits"."""
+    import hashlib
+    h = hashlib.sha256()
+    g = scene.gaussians
+    for t in (g.means, g.covariances, g.harmonics, g.opacities, scene.grad_color, scene.grad_depth):
+        h.update(t.detach().contiguous().numpy().tobytes())
+    B, V = scene.extrinsics.shape[:2]
+    for b in range(B):
+        for v in range(V):
+            for k, a in sorted(per_view_extension_inputs(scene, b, v).items()):
+                h.update(np.ascontiguousarray(a).tobytes() if isinstance(a, np.ndarray) else repr(a).encode())
+    return h.hexdigest()
+
+
 def rel_err(a, b, floor=None):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     scale = max(np.abs(b).max(), 1e-30) if floor is None else floor
