@@ -6,6 +6,7 @@ importing the ops raises.  Build it with ``python -m my_depthsplat_b200.build`` 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -155,6 +156,11 @@ def load() -> C.CDLL:
     L.b200s_debug_set.argtypes = [C.c_int, C.c_int]
     if L.b200s_abi_version() != ABI_VERSION:
         raise LibraryMissing(f"{LIB_PATH} has ABI {L.b200s_abi_version()}, expected {ABI_VERSION}; rebuild it")
+    # debug only: kernel variant switches for A/B runs ("2=1,3=1" -> b200s_debug_set(2, 1), b200s_debug_set(3, 1));
+    # variants never change results
+    for kv in filter(None, os.environ.get("B200S_KNOBS", "").split(",")):
+        k, v = kv.split("=")
+        L.b200s_debug_set(int(k), int(v))
     _lib = L
     return L
 

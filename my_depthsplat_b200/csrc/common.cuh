@@ -84,6 +84,35 @@ __device__ __forceinline__ void load_view_params(ViewParams& vp, const B200sView
   vp.scene = v.scene_index[view];
 }
 
+// The camera blocks of `count` consecutive views [view0, view0 + count) loaded by the whole CTA at once (one field per
+// thread: one memory latency for the group instead of ~50 dependent-issue loads by one thread per view).  Same values,
+// same expressions as load_view_params.  Callers synchronise before reading.
+constexpr int VIEW_GROUP = 8;
+__device__ __forceinline__ void load_view_group(ViewParams* vps, const B200sViews& v, int view0, int count, int H, int W) {
+  for (int t = threadIdx.x; t < count * 64; t += blockDim.x) {
+    const int f = t & 63, view = view0 + (t >> 6);
+    ViewParams& p = vps[t >> 6];
+    if (f < 16) p.view[f] = v.viewmatrix[view * 16 + f];
+    else if (f < 32) p.proj[f - 16] = v.projmatrix[view * 16 + f - 16];
+    else if (f < 35) p.campos[f - 32] = v.campos[view * 3 + f - 32];
+    else if (f < 38) p.bg[f - 35] = v.background[view * 3 + f - 35];
+    else if (f == 38) { const float t_ = v.tanfov[view * 2]; p.tanfovx = t_; p.focal_x = (float)W / (2.0f * t_); }
+    else if (f == 39) { const float t_ = v.tanfov[view * 2 + 1]; p.tanfovy = t_; p.focal_y = (float)H / (2.0f * t_); }
+    else if (f == 40) p.s = v.scale ? v.scale[view * 2] : 1.0f;
+    else if (f == 41) p.s2 = v.scale ? v.scale[view * 2 + 1] : 1.0f;
+    else if (f < 46) p.daff[f - 42] = v.depth_affine ? v.depth_affine[view * 4 + f - 42] : 0.f;
+    else if (f == 46) p.dnear = v.depth_clamp ? v.depth_clamp[view * 2] : 0.f;
+    else if (f == 47) p.dfar = v.depth_clamp ? v.depth_clamp[view * 2 + 1] : 0.f;
+    else if (f == 48) p.scene = v.scene_index[view];
+  }
+}
+// [first, last] view index of `scene` (its views need not be contiguous: views of other scenes in between are skipped by
+// the callers).  Shared words lo / hi are initialised by the caller before a barrier; call, then barrier, then read.
+__device__ __forceinline__ void scene_view_range(const B200sViews& v, int num_views, int scene, int* lo, int* hi) {
+  for (int t = threadIdx.x; t < num_views; t += blockDim.x)
+    if (v.scene_index[t] == scene) { atomicMin(lo, t); atomicMax(hi, t); }
+}
+
 // p1 + p2 + p3 with the contraction nvcc applies (second product plain, first fused, third fused)
 __device__ __forceinline__ float dot3c(float a, float b, float c, float d, float e, float f) {
   return __fmaf_rn(e, f, __fmaf_rn(a, b, __fmul_rn(c, d)));

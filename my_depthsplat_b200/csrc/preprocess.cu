@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
   constexpr bool SPECIALISED = MODE != 0;
   constexpr bool RAW = MODE == 2;
   extern __shared__ __align__(16) float smem[];
-  __shared__ ViewParams vp;
-  __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
+  __shared__ ViewParams s_vp[VIEW_GROUP];
+  __shared__ uint32_t s_tot[VIEW_GROUP];
+  __shared__ int s_vlo, s_vhi;
   __shared__ __align__(8) uint64_t s_bar;
 
   const int cov_floats = SPECIALISED ? 9 : a.cov_floats;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
   float* s_cov = s_mean + PRE_THREADS * 3;               // [256*cov_floats]
   float* s_op = s_cov + PRE_THREADS * cov_floats;        // [256]
   float* s_col = s_op + PRE_THREADS;                     // [256*col_stride]
-  float4* s_rec = reinterpret_cast<float4*>(s_col + PRE_THREADS * col_stride);  // [256*4] record staging
+  if (tid == 0) { s_vlo = 0x7fffffff; s_vhi = -1; }      // ordered before the range search by the barriers of the staging below
   float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, opac = 0.f;
   if (RAW) {
     // ---- stage the 41 raw planes of the chunk (37 head channels, depth, 3 image channels), run the adapter -----------
@@ -208,11 +209,20 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
   }
   const float* cs = s_col + tid * col_stride;
 
-  for (int view = 0; view < a.VV; view++) {
-    if (vw.scene_index[view] != scene) continue;  // block-uniform
-    __syncthreads();  // the previous view's readers of vp / s_rec / s_warp_tot are done
-    if (tid == 0) load_view_params(vp, vw, view, a.H, a.W);
-    __syncthreads();
+  // ---- the views of the scene, VIEW_GROUP camera blocks at a time; no barrier inside a group: the warps run free ----
+  scene_view_range(vw, a.VV, scene, &s_vlo, &s_vhi);
+  __syncthreads();
+  const int vlo = s_vlo, vhi = s_vhi;
+  for (int v0 = vlo; v0 <= vhi; v0 += VIEW_GROUP) {
+  const int vcount = min(VIEW_GROUP, vhi + 1 - v0);
+  if (v0 != vlo) __syncthreads();  // the previous group's readers of s_vp / s_tot are done
+  load_view_group(s_vp, vw, v0, vcount, a.H, a.W);
+  if (tid < VIEW_GROUP) s_tot[tid] = 0u;
+  __syncthreads();
+  for (int vj = 0; vj < vcount; vj++) {
+    const ViewParams& vp = s_vp[vj];
+    if (vp.scene != scene) continue;  // block-uniform
+    const int view = v0 + vj;
     const int ticket = chunk * a.VV + view;
 
     // ---- per-Gaussian projection -------------------------------------------------------------
@@ -306,19 +316,16 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) project_kernel(const B200sScen
     uint32_t sum = tiles;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    if (lane == 0) s_warp_tot[warp] = sum;
     const uint32_t vis_mask = __ballot_sync(0xffffffffu, tiles > 0);
-    if (lane == 0 && vis_mask) atomicAdd(&a.status->num_visible, (uint32_t)__popc(vis_mask));
-    s_rec[tid * 4 + 0] = out.q0; s_rec[tid * 4 + 1] = out.q1; s_rec[tid * 4 + 2] = out.q2; s_rec[tid * 4 + 3] = out.q3;
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t t = 0;
-#pragma unroll
-      for (int w = 0; w < PRE_THREADS / 32; w++) t += s_warp_tot[w];
-      a.ticket_totals[ticket] = t;
+    if (lane == 0 && vis_mask) { atomicAdd(&s_tot[vj], sum); atomicAdd(&a.status->num_visible, (uint32_t)__popc(vis_mask)); }
+    // the thread's own 64-byte record, four 16-byte stores (two full sectors per thread; L2 merges the halves)
+    if (tid < n) {
+      float4* dst = reinterpret_cast<float4*>(a.rec + (long long)view * a.N + i0 + tid);
+      dst[0] = out.q0; dst[1] = out.q1; dst[2] = out.q2; dst[3] = out.q3;
     }
-    float4* dst = reinterpret_cast<float4*>(a.rec + (long long)view * a.N + i0);
-    for (int i = tid; i < n * 4; i += PRE_THREADS) dst[i] = s_rec[i];
+  }
+  __syncthreads();  // the group's tile totals are complete
+  if (tid < vcount && s_vp[tid].scene == scene) a.ticket_totals[chunk * a.VV + v0 + tid] = s_tot[tid];
   }
 }
 
@@ -616,7 +623,7 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   a.col_floats = sc.colors_precomp ? 3 : 3 * sc.sh_coeffs;
   a.col_stride = a.col_floats | 1;
   a.fpg = 3 + a.cov_floats + 1 + a.col_stride;
-  // raw scenes: the 41 staged planes (41 KB) share the specialised layout's 40 KB + record staging (they are dead before the records are written)
+  // raw scenes: the 41 staged planes are dead (in registers) before the specialised layout's 40 KB overwrite them
   if (sc.raw_head) { a.cov_floats = 9; a.col_floats = 27; a.col_stride = 27; a.fpg = 40; }
   a.rec = reinterpret_cast<Rec*>(saved + plan.off_rec);
   // the sort ping-pongs `sort_passes` times and must end in the A buffers
@@ -646,8 +653,10 @@ cudaError_t launch_preprocess_bin(const B200sScene& sc, const B200sViews& vw, co
   if ((e = cudaMemsetAsync(a.scan_blocks, 0, (size_t)scan_blocks * sizeof(uint64_t), stream)) != cudaSuccess) return e;
   if (binned) { if ((e = cudaMemsetAsync(a.bin_count, 0, (size_t)plan.bins * sizeof(uint32_t), stream)) != cudaSuccess) return e; }
   else if ((e = cudaMemsetAsync(a.hist, 0, 8 * 256 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
-  const size_t smem = (size_t)PRE_THREADS * a.fpg * sizeof(float) + (size_t)PRE_THREADS * sizeof(Rec);
   const bool raw = sc.raw_head != nullptr;
+  // the staged chunk only (raw scenes: the 41 planes, overwritten by the specialised layout once they are in registers);
+  // records go straight to global memory
+  const size_t smem = (size_t)PRE_THREADS * (raw ? RAW_PLANES : a.fpg) * sizeof(float);
   const bool specialised = raw || (sc.cov_layout == B200S_COV_3X3 && !sc.colors_precomp && sc.sh_layout == B200S_SH_CHANNEL_MAJOR &&
                                    sc.sh_coeffs == 9 && sc.sh_degree == 2);
   // the attribute is per (function, device) and cheap to set: no cache that a second device or thread could get wrong

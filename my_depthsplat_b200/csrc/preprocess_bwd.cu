@@ -78,7 +78,8 @@ template <int NC, bool MC, bool RAW = false>
 __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B200sScene sc, const B200sViews vw, const B200sGradIn gin,
                                                                      const PreBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ ViewParams vp;
+  __shared__ ViewParams s_vp[VIEW_GROUP];
+  __shared__ int s_vlo, s_vhi;
   __shared__ __align__(8) uint64_t s_bar;
   if (*a.overflow) return;
   constexpr int DEG = NC == 16 ? 3 : (NC == 9 ? 2 : (NC == 4 ? 1 : 0));
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
   float* s_mean = smem;
   float* s_cov = s_mean + PRE_THREADS * 3;
   float* s_col = s_cov + PRE_THREADS * a.cov_floats;
+  if (tid == 0) { s_vlo = 0x7fffffff; s_vhi = -1; }  // ordered before the range search by the barriers of the staging below
   float mraw[3] = {0.f, 0.f, 0.f}, craw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float op = 0.f;
   __shared__ RawCam s_cam;
@@ -172,23 +174,57 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
 #pragma unroll
   for (int k = 0; k < NACC; k++) dcol[k] = 0.f;
 
-  for (int view = 0; view < a.VV; view++) {
-    if (vw.scene_index[view] != scene) continue;  // block-uniform
-    __syncthreads();
-    if (tid == 0) load_view_params(vp, vw, view, a.H, a.W);
-    __syncthreads();
-    if (tid >= n) continue;
-    const size_t ri = (size_t)view * a.N + i0 + tid;
+  // ---- the views of the scene, VIEW_GROUP camera blocks at a time; no barrier inside a group.  The (view, Gaussian)
+  // record and gradient record of the NEXT view are requested before the current view is worked on: one memory latency
+  // per view is hidden behind the arithmetic instead of two exposed ones (record -> radius -> gradient record). ----
+  scene_view_range(vw, a.VV, scene, &s_vlo, &s_vhi);
+  __syncthreads();
+  const int vlo = s_vlo, vhi = s_vhi;
+  const size_t rstride = (size_t)a.N;
+  const bool have = tid < n;
+  float2 nq3 = make_float2(0.f, 0.f);   // (radius bits, flags bits) of the next view of the scene
+  float4 ng0 = make_float4(0.f, 0.f, 0.f, 0.f), ng1 = ng0;
+  float2 ng2 = make_float2(0.f, 0.f);
+  auto fetch = [&](int view) {
+    // invisible (view, Gaussian) pairs hold zeros in their gradient record (the buffer is cleared before the compositing
+    // backward): loading it unconditionally costs no correctness and frees the load from the radius
+    const size_t ri = (size_t)view * rstride + i0 + tid;
     const float4 q3 = __ldg(&a.rec[ri].q3);
-    const int radius = __float_as_int(q3.y);
+    nq3 = make_float2(q3.y, q3.w);
     const float4* gp = reinterpret_cast<const float4*>(a.grad_rec + ri * GREC_FLOATS);
-    float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, g2v = g0v;
-    if (radius > 0) { g0v = __ldg(gp); g1v = __ldg(gp + 1); g2v = __ldg(gp + 2); }
+    ng0 = __ldg(gp); ng1 = __ldg(gp + 1);
+    ng2 = __ldg(reinterpret_cast<const float2*>(gp + 2));
+  };
+  for (int v0 = vlo; v0 <= vhi; v0 += VIEW_GROUP) {
+  const int vcount = min(VIEW_GROUP, vhi + 1 - v0);
+  if (v0 != vlo) __syncthreads();  // the previous group's readers of s_vp are done
+  load_view_group(s_vp, vw, v0, vcount, a.H, a.W);
+  __syncthreads();
+  if (have) {
+    int vfirst = 0;
+    while (vfirst < vcount && s_vp[vfirst].scene != scene) vfirst++;
+    if (vfirst < vcount) fetch(v0 + vfirst);
+  }
+  for (int vj = 0; vj < vcount; vj++) {
+    const ViewParams& vp = s_vp[vj];
+    if (vp.scene != scene) continue;  // block-uniform
+    if (!have) continue;
+    const int view = v0 + vj;
+    const size_t ri = (size_t)view * rstride + i0 + tid;
+    const float2 q3yw = nq3;
+    const float4 g0v = ng0, g1v = ng1;
+    const float4 g2v = make_float4(ng2.x, ng2.y, 0.f, 0.f);
+    {
+      int vn = vj + 1;
+      while (vn < vcount && s_vp[vn].scene != scene) vn++;
+      if (vn < vcount) fetch(v0 + vn);
+    }
+    const int radius = __float_as_int(q3yw.x);
     if (radius <= 0) {
       if (a.dL_dmeans2D) { float* o = a.dL_dmeans2D + ri * 3; o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
       continue;
     }
-    const uint32_t flags = __float_as_uint(q3.w);
+    const uint32_t flags = __float_as_uint(q3yw.y);
     dop += g1v.y;
     const float m[3] = {__fmul_rn(mraw[0], vp.s), __fmul_rn(mraw[1], vp.s), __fmul_rn(mraw[2], vp.s)};
     float c6[6];
@@ -328,6 +364,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B2
       }
       dmean[0] += vp.daff[0] * dz; dmean[1] += vp.daff[1] * dz; dmean[2] += vp.daff[2] * dz;
     }
+  }
   }
 
   if (RAW) {

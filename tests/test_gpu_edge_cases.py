@@ -184,7 +184,9 @@ def test_workspace_budget_splits_the_views_and_changes_nothing():
         R._capacity_hint.clear()
     assert torch.equal(got, ref)
     for a, b in ((g1.means, g0.means), (g1.covariances, g0.covariances), (g1.harmonics, g0.harmonics), (g1.opacities, g0.opacities)):
-        torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-6 * float(b.grad.abs().max()))
+        # the compositing backward accumulates with REDs (order varies from run to run) and the split sums the views in
+        # another order: a few 1e-6 of the gradient scale apart, an order below the 1e-4 bar
+        torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-5 * float(b.grad.abs().max()))
 
 
 def test_camera_block_graph_replays_the_eager_sequence_bit_for_bit():
