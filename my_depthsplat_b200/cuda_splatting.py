@@ -205,6 +205,22 @@ def render_views(
     except PairLimitExceeded:
         if V == 1 and B == 1:
             raise
+    # the parts of a split call give their workspaces back after the forward and rebuild them in the backward
+    # (rasterizer.remat_depth): the workspace bound of one call then bounds the whole step
+    from . import rasterizer as _R
+    _R.remat_depth += 1
+    try:
+        return _render_views_split(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means, gaussian_covariances,
+                                   gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode, want_radii, count_work,
+                                   grad_reducer, mse)
+    finally:
+        _R.remat_depth -= 1
+
+
+def _render_views_split(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means, gaussian_covariances,
+                        gaussian_sh_coefficients, gaussian_opacities, scale_invariant, use_sh, depth_mode, want_radii, count_work,
+                        grad_reducer, mse):
+    B, V = extrinsics.shape[:2]
     if V == 1:  # one view per scene: split the SCENES instead
         hb = B // 2
         bsl = (slice(0, hb), slice(hb, B))

@@ -161,8 +161,18 @@ class PairLimitExceeded(RuntimeError):
 # the pair count asks for (110 GB for two views in round 1).  A call whose MEASURED pair count needs more than this and has
 # more than one view raises PairLimitExceeded, so that the views are rendered in smaller groups; a single view is always
 # rendered, whatever it needs.
-max_workspace_bytes = int(float(os.environ.get("B200S_MAX_WORKSPACE_GB", "40")) * 1e9)
+max_workspace_bytes = int(float(os.environ.get("B200S_MAX_WORKSPACE_GB", "32")) * 1e9)
 _BYTES_PER_PAIR = 24
+
+# Rematerialisation.  A call that had to be split to stay inside max_workspace_bytes would otherwise keep the forward->backward
+# workspace of EVERY part alive until the backward (sorted lists: 4 bytes per pair -- 5 GB per view of the stress config),
+# so the bound on one call would not bound the step.  While ``remat_depth`` > 0 (cuda_splatting.render_views raises it
+# around the parts of a split call) a differentiable forward gives its workspace back at once and the backward rebuilds it:
+# binning, sort and compositing forward run again from the same inputs at the same capacity -- deterministic kernels, the
+# lists, final_T and n_contrib come out bit for bit as they were -- and then the backward proper.  Peak memory of the step
+# = one part's workspaces; cost = one more forward per part.
+remat_depth = 0
+remat_count = 0   # backward passes that rebuilt their workspace (tests, diagnostics)
 
 
 class _HostStatusRing:
@@ -200,13 +210,20 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def _with_slack(nbytes: int, frac: float) -> int:
+    """Buffers are allocated a little larger than asked so that a slightly bigger next call reuses them -- by a fraction for
+    ordinary sizes, by at most 256 MB for the multi-GB workspaces of a stress scene (max_workspace_bytes bounds what is
+    ASKED for; the slack must not add gigabytes on top)."""
+    return nbytes + min(int(nbytes * frac), 256 << 20) + 4096
+
+
 def _scratch(device, nbytes: int) -> torch.Tensor:
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     buf = _scratch_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None
         _scratch_cache.pop(key, None)
-        buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)
+        buf = torch.empty(_with_slack(nbytes, 0.10), dtype=torch.uint8, device=device)
         _scratch_cache[key] = buf
     return buf
 
@@ -228,7 +245,7 @@ class _SavedLease:
         if best is not None and pool[best].numel() <= 2 * nbytes + (1 << 20):
             self.tensor = pool.pop(best)
         else:
-            self.tensor = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
+            self.tensor = torch.empty(_with_slack(nbytes, 0.05), dtype=torch.uint8, device=device)
 
     def __del__(self):
         try:
@@ -349,8 +366,11 @@ class _Rasterize(torch.autograd.Function):
         else:
             cap = _capacity_hint.get(key) or max(4 * N * VV, 1 << 16)
             cap = min(cap, _PAIR_LIMIT)
-            if VV > 1:  # the first, speculative attempt stays inside the budget too
-                cap = max(min(cap, (max_workspace_bytes - VV * (N * 72 + H * W * 8)) // _BYTES_PER_PAIR), 1 << 16)
+            # the first, speculative attempt stays inside the budget too (a single view: unless it is known to need more)
+            budget_pairs = (max_workspace_bytes - VV * (N * 72 + H * W * 8)) // _BYTES_PER_PAIR
+            if VV == 1:
+                budget_pairs = max(budget_pairs, _max_pairs.get(key, 0) + 4096)
+            cap = max(min(cap, budget_pairs), 1 << 16)
         words = _status_ring.words
         retries = 0
         while True:
@@ -390,8 +410,9 @@ class _Rasterize(torch.autograd.Function):
                 raise PairLimitExceeded(f"{num_pairs} (tile, Gaussian) pairs for {VV} views need {num_pairs * _BYTES_PER_PAIR / 1e9:.1f} GB of pair buffers, "
                                         f"more than max_workspace_bytes = {max_workspace_bytes / 1e9:.0f} GB; render fewer views per call")
             cap = min(int(num_pairs * 1.25) + 4096, _PAIR_LIMIT)
-            if VV > 1:
-                cap = min(cap, max((max_workspace_bytes - VV * (N * 72 + H * W * 8)) // _BYTES_PER_PAIR, num_pairs))
+            # the measured count is exact: the 25 % head-room shrinks to whatever the budget leaves (a single view is rendered
+            # whatever it needs, but asks for no more than it needs once the budget is exceeded)
+            cap = min(cap, max((max_workspace_bytes - VV * (N * 72 + H * W * 8)) // _BYTES_PER_PAIR, num_pairs + 4096))
             retries += 1
         if not lazy:
             _note_pairs(key, num_pairs)
@@ -408,6 +429,10 @@ class _Rasterize(torch.autograd.Function):
             global debug_last
             debug_last = dict(plan=plan, saved=saved, scratch=scratch, num_pairs=num_pairs, N=N, VV=VV, H=H, W=W)
         ctx.save_for_backward(means, covs, colors, opacities)
+        ctx.remat = None
+        if remat_depth > 0 and not lazy and not debug_keep and any(ctx.needs_input_grad[:4]):
+            ctx.remat = True
+            lease = None   # back to the pool now; the backward takes a fresh one and rebuilds its contents
         ctx.b200 = (vp, use_sh, sh_degree, sh_layout, plan, lease, means2d is not None, pending)
         ctx.set_materialize_grads(False)
         ctx.mse_grad = mse_grad
@@ -438,12 +463,26 @@ class _Rasterize(torch.autograd.Function):
         vp, use_sh, sh_degree, sh_layout, plan, lease, want_m2d, pending = ctx.b200
         if pending is not None:
             pending.check(block=True)  # lazy mode: the forward's status word, normally long since written
-        saved = lease.tensor
         dev = means.device
         raw = ctx.raw
         VV, N = vp.scene_index.shape[0], (means.shape[1] if raw is None else raw.views * raw.height * raw.width)
         stream = torch.cuda.current_stream(dev).cuda_stream
         sc, vw = _build_structs(means, covs, colors, opacities, use_sh, sh_degree, sh_layout, vp, raw)
+        if ctx.remat is not None:
+            global remat_count
+            remat_count += 1
+            # rebuild the forward->backward workspace: same inputs, same capacity, same sort mode -> same lists, final_T,
+            # n_contrib (the images go to a throw-away buffer; the fused loss is not evaluated again)
+            lease = _SavedLease(dev, plan.saved_bytes)
+            tmp_color = torch.empty((VV, 3, vp.height, vp.width), dtype=torch.float32, device=dev)
+            tmp_depth = torch.empty((VV, vp.height, vp.width), dtype=torch.float32, device=dev) if vp.depth_mode is not None else None
+            _slot, slot_ptr = _status_ring.take()
+            fout = _lib.Out(_ptr(tmp_color), _ptr(tmp_depth), None, 0, slot_ptr)
+            scratch = _scratch(dev, plan.scratch_bytes)
+            for fn, what in ((L.b200s_forward_bin, "b200s_forward_bin (remat)"), (L.b200s_forward_render, "b200s_forward_render (remat)")):
+                _lib.check(fn(C.byref(sc), C.byref(vw), C.byref(plan), lease.tensor.data_ptr(), scratch.data_ptr(), C.byref(fout), stream), what)
+            del tmp_color, tmp_depth
+        saved = lease.tensor
         g_color = (torch.zeros((VV, 3, vp.height, vp.width), dtype=torch.float32, device=dev) if g_color is None
                    else g_color.to(torch.float32).contiguous())
         if vp.depth_mode is not None:

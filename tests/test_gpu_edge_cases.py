@@ -175,10 +175,14 @@ def test_workspace_budget_splits_the_views_and_changes_nothing():
     H, W = scene.image_shape
     # room for the records of all four views but for the pairs of about one
     R.max_workspace_bytes = 4 * (N * 72 + H * W * 8) + (pairs // 3) * 24
+    remat0 = R.remat_count
     try:
         got, _ = _render(scene, g1)
         assert R.last_stats.num_pairs < pairs           # the last call rendered a subset of the views
         (got * scene.grad_color.cuda()).sum().backward()
+        # the parts gave their forward->backward workspaces back after the forward and rebuilt them in the backward
+        # (rasterizer.remat_depth): the bound on one call bounds the step
+        assert R.remat_count - remat0 >= 2
     finally:
         R.max_workspace_bytes = old
         R._capacity_hint.clear()
