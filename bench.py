@@ -491,6 +491,9 @@ def run_ours(args):
             gpu_baseline = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
+        _red = getattr(ranged if by_range else sharded, "reducer", None)
+        pull_desc = ("peer loads over NVLink summed in registers" if getattr(_red, "pull", "p2p") == "p2p"
+                     else "multimem.ld_reduce on the NVLS multicast address")
         line = {
             "metric": "rasterizer fwd+bwd Mpix/s", "value": round(value, 2), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": W_, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -499,8 +502,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (Gaussians 472 MB + 64 B records per view)" if N * 160 > 126e6 else "inputs fit L2",
                        "parallelism": (f"scene-sharded x{world}: {B_local} scene(s) per GPU, no collective on the rendering path") if by_scene else
                        (f"view-sharded x{world}, Gaussians sharded by range ({N // world} per rank): NCCL all-gather over NVLink in the forward, "
-                        + ("NCCL reduce-scatter" if args.nccl_scatter else f"reduce-scatter by the library's NVLS kernel (multimem.ld_reduce) in {args.pieces} pieces under the projection backward")
-                        + " of the per-Gaussian gradients in the backward") if by_range else f"view-sharded x{world} ({'contiguous' if args.contiguous_views else 'interleaved'} views), Gaussians replicated" + (f", per-Gaussian gradients reduce-scattered by Gaussian range (library NVLS kernel, {args.pieces} pieces under the projection backward)" if scatter else "") + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
+                        + ("NCCL reduce-scatter" if args.nccl_scatter else f"reduce-scatter by the library's own kernel ({pull_desc}) in {args.pieces} pieces under the projection backward")
+                        + " of the per-Gaussian gradients in the backward") if by_range else f"view-sharded x{world} ({'contiguous' if args.contiguous_views else 'interleaved'} views), Gaussians replicated" + (f", per-Gaussian gradients reduce-scattered by Gaussian range (library kernel: {pull_desc}; {args.pieces} pieces under the projection backward)" if scatter else "") + ((", per-Gaussian grads summed in-kernel over NVLS multicast (multimem.red)" if args.fused_reduce
                                         else ("" if scatter else ", NCCL all-reduce of per-Gaussian grads" + (" in 2 chunks overlapped with the projection backward" if args.overlap_reduce else ""))) if world > 1 else "")},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_step_e, 4), "pinned_copy_bandwidth": pcie, "allocator_events": alloc_events,

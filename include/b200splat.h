@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200S_ABI_VERSION 10
+#define B200S_ABI_VERSION 11
 
 enum { B200S_OK = 0, B200S_EBADARG = 1, B200S_ECUDA = 3 };
 
@@ -225,6 +225,14 @@ typedef struct B200sGradIn { /* all fp32, OVERWRITTEN (summed over the views of 
  * (all replicas complete). */
 int b200s_nvls_reduce_segments(void* multicast_base, void* local_base, const unsigned long long* seg_offset,
                                const unsigned long long* seg_count, int nseg, void* stream);
+
+/* The same share of the reduce-scatter by ordinary peer loads instead of the switch's reduction: peer_bases[r] (HOST array of
+ * `world` device pointers, 2 <= world <= 16) is rank r's replica of the symmetric buffer as mapped into the calling process
+ * (peer_bases[rank] = the caller's own); for every vector of the segments the caller reads all replicas (own first, then
+ * ranks rank+1, rank+2, ... mod world: a fixed summation order), and stores the sum at the same offset of local_base.  Moves
+ * (world-1)/world of the buffer per GPU over NVLink where the multimem pull moves all of it. */
+int b200s_p2p_reduce_segments(const void* const* peer_bases, int world, int rank, void* local_base, const unsigned long long* seg_offset,
+                              const unsigned long long* seg_count, int nseg, void* stream);
 
 /* Pure host function: fills the plan for the given dimensions.  No CUDA calls. */
 int b200s_plan(const B200sDims* dims, B200sPlan* plan);

@@ -11,7 +11,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200splat.so"
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 B200S_OK, B200S_EBADARG, B200S_ECUDA = 0, 1, 3
 COV_3X3, COV_UPPER6 = 0, 1
@@ -93,7 +93,7 @@ class GradIn(C.Structure):
 EXPORTS = (
     "b200s_plan", "b200s_forward_bin", "b200s_forward_render", "b200s_backward", "b200s_sort_tmp_bytes",
     "b200s_sort_pairs", "b200s_abi_version", "b200s_last_cuda_error", "b200s_build_info", "b200s_profile_enable",
-    "b200s_profile_read", "b200s_kernel_launches", "b200s_debug_set", "b200s_host_alloc", "b200s_host_free",
+    "b200s_profile_read", "b200s_kernel_launches", "b200s_debug_set", "b200s_p2p_reduce_segments", "b200s_host_alloc", "b200s_host_free",
     "b200s_nvls_allreduce", "b200s_nvls_reduce_segments", "b200s_segment_sort", "b200s_segment_sort_tmp_bytes",
 )
 STAGES = ("pre_bin", "sort_hist", "sort_passes", "ranges", "comp_fwd", "grad_zero", "comp_bwd", "pre_bwd", "end", "bin_sort")
@@ -148,6 +148,8 @@ def load() -> C.CDLL:
     L.b200s_nvls_allreduce.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int, C.c_void_p]
     L.b200s_nvls_reduce_segments.restype = C.c_int
     L.b200s_nvls_reduce_segments.argtypes = [vp, vp, P(C.c_ulonglong), P(C.c_ulonglong), C.c_int, vp]
+    L.b200s_p2p_reduce_segments.restype = C.c_int
+    L.b200s_p2p_reduce_segments.argtypes = [P(C.c_void_p), C.c_int, C.c_int, vp, P(C.c_ulonglong), P(C.c_ulonglong), C.c_int, vp]
     L.b200s_segment_sort_tmp_bytes.restype = C.c_size_t
     L.b200s_segment_sort_tmp_bytes.argtypes = [C.c_int64, C.c_int32]
     L.b200s_segment_sort.restype = C.c_int

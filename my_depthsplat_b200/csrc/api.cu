@@ -119,6 +119,20 @@ int b200s_nvls_reduce_segments(void* multicast_base, void* local_base, const uns
   return e == cudaSuccess ? B200S_OK : fail(e);
 }
 
+int b200s_p2p_reduce_segments(const void* const* peer_bases, int world, int rank, void* local_base, const unsigned long long* seg_offset,
+                              const unsigned long long* seg_count, int nseg, void* stream) {
+  if (!peer_bases || !local_base || !seg_offset || !seg_count || nseg <= 0 || nseg > 16 || world < 2 || world > 16 || rank < 0 || rank >= world)
+    return B200S_EBADARG;
+  if (reinterpret_cast<uintptr_t>(local_base) & 15) return B200S_EBADARG;
+  for (int k = 0; k < world; k++)
+    if (!peer_bases[k] || (reinterpret_cast<uintptr_t>(peer_bases[k]) & 15)) return B200S_EBADARG;
+  for (int i = 0; i < nseg; i++)
+    if ((seg_offset[i] | seg_count[i]) & 3ull) return B200S_EBADARG;
+  const cudaError_t e = b200s::launch_p2p_reduce_segments(peer_bases, world, rank, static_cast<float*>(local_base), seg_offset, seg_count, nseg,
+                                                          sm_count(), static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? B200S_OK : fail(e);
+}
+
 int b200s_plan(const B200sDims* d, B200sPlan* p) {
   if (!d || !p) return B200S_EBADARG;
   if (d->num_scenes <= 0 || d->num_gaussians <= 0 || d->num_views <= 0 || d->height <= 0 || d->width <= 0) return B200S_EBADARG;

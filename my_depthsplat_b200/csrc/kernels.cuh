@@ -45,6 +45,8 @@ void count_launches(int n);
 cudaError_t launch_nvls_allreduce(float* multicast, unsigned long long n_floats, int rank, int world, int sm_count, cudaStream_t stream);
 cudaError_t launch_nvls_reduce_segments(const float* multicast, float* local, const unsigned long long* off, const unsigned long long* cnt, int nseg,
                                         int sm_count, cudaStream_t stream);
+cudaError_t launch_p2p_reduce_segments(const void* const* peers, int world, int rank, float* local, const unsigned long long* off,
+                                       const unsigned long long* cnt, int nseg, int sm_count, cudaStream_t stream);
 extern std::atomic<int> g_sort_knobs[4];  // A/B switches of b200s_debug_set (debug only; never change results)
 int device_sm_count();                                       // of the current device, cached per device id
 bool first_use_on_device(std::atomic<unsigned long long>& seen);  // true once per (call site's mask, current device)

@@ -21,6 +21,7 @@ given the Gaussians, so the path shards without any data-path collective:
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional, Sequence
 
 import torch
@@ -326,7 +327,15 @@ class RangeScatterReducer:
     scatter = True
     ROTATE = 3
 
-    def __init__(self, group: Optional[dist.ProcessGroup] = None, pieces: int = 4):
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, pieces: int = 4, pull: Optional[str] = None):
+        # how a rank gets the sum of its share of a piece: "p2p" (default) = ordinary loads from every peer's replica of the
+        # symmetric buffer, summed in registers (b200s_p2p_reduce_segments) -- (N-1)/N of the buffer per GPU over NVLink in
+        # coalesced requests; "nvls" = multimem.ld_reduce on the multicast address (b200s_nvls_reduce_segments) -- the
+        # switch reads EVERY replica, the caller's own included: the whole buffer leaves every GPU per step, in 16-byte
+        # requests (N = 2: 0.84 ms of pulls per step against 0.35 ms; tools/dist_timeline.py)
+        self.pull = (pull or os.environ.get("B200S_SCATTER_PULL", "p2p")).lower()
+        if self.pull not in ("p2p", "nvls"):
+            raise ValueError("pull must be 'p2p' or 'nvls'")
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(self.group) if dist.is_initialized() else 0
@@ -344,7 +353,7 @@ class RangeScatterReducer:
             import torch.distributed._symmetric_memory as symm_mem
             t = symm_mem.empty(1024, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
             h = symm_mem.rendezvous(t, self.group)
-            return bool(h.multicast_ptr)
+            return bool(h.multicast_ptr) if self.pull == "nvls" else len(h.buffer_ptrs) == self.world
         except Exception:
             return False
 
@@ -364,7 +373,7 @@ class RangeScatterReducer:
             for _ in range(self.ROTATE):
                 t = symm_mem.empty(o, dtype=torch.float32, device=device)
                 h = symm_mem.rendezvous(t, self.group)
-                if not h.multicast_ptr:
+                if self.pull == "nvls" and not h.multicast_ptr:
                     self.available = False
                     raise RuntimeError("no NVLS multicast on this fabric")
                 t.zero_()
@@ -394,12 +403,20 @@ class RangeScatterReducer:
         blocks = (self._N + 255) // 256
         per_rank = (blocks + self.world - 1) // self.world
         k = self.num_pieces
-        per_piece = (per_rank + k - 1) // k
-        out = []
-        for j in range(k):
-            cn = min(per_piece, per_rank - j * per_piece)
-            if cn > 0:
-                out.append((j * per_piece, cn, per_rank, self.world))
+        # EVEN pieces.  Measured at N = 2 (tools/dist_timeline.py): the pulls, not the kernels, are the longer chain -- every
+        # GPU's replica crosses its NVLink once per step whatever N is (the switch reads all replicas), ~0.8 ms at the
+        # ~600 GB/s the 16-byte multimem requests reach -- so decreasing sizes (last, un-hidden pull smallest) gain nothing
+        # (5.61 against 5.60 ms), and more than four pieces lose to the tails of the shorter kernels (8: 5.60, 16: 5.82 ms
+        # against 5.55 ms)
+        weights = list(range(k, 0, -1)) if os.environ.get("B200S_PIECE_WEIGHTS", "even") == "dec" else [1] * k
+        out, c0 = [], 0
+        for j, wgt in enumerate(weights):
+            left = per_rank - c0
+            if left <= 0:
+                break
+            cn = left if j == k - 1 else min(left, max(1, -(-per_rank * wgt // sum(weights))))
+            out.append((c0, cn, per_rank, self.world))
+            c0 += cn
         self._per_rank = per_rank
         return out
 
@@ -426,12 +443,17 @@ class RangeScatterReducer:
                     if a1 > a0:
                         segs.append((a0, a1 - a0))
             L = _lib.load()
+            peers = (C.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs]) if self.pull == "p2p" else None
             for i in range(0, len(segs), 16):
                 part = segs[i:i + 16]
                 so = (C.c_ulonglong * len(part))(*[p[0] for p in part])
                 sn = (C.c_ulonglong * len(part))(*[p[1] for p in part])
-                _lib.check(L.b200s_nvls_reduce_segments(h.multicast_ptr, self._out.data_ptr(), so, sn, len(part), self._side.cuda_stream),
-                           "b200s_nvls_reduce_segments")
+                if peers is not None:
+                    _lib.check(L.b200s_p2p_reduce_segments(peers, self.world, self.rank, self._out.data_ptr(), so, sn, len(part),
+                                                           self._side.cuda_stream), "b200s_p2p_reduce_segments")
+                else:
+                    _lib.check(L.b200s_nvls_reduce_segments(h.multicast_ptr, self._out.data_ptr(), so, sn, len(part), self._side.cuda_stream),
+                               "b200s_nvls_reduce_segments")
 
     def end(self):
         """-> the gradient tensors: this rank's Gaussian range summed over all ranks, zero elsewhere."""

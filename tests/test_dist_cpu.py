@@ -168,3 +168,25 @@ def test_render_clip_rejects_host_streaming_without_cuda_and_with_gather():
         render_clip(*args, to_host=True)             # CPU tensors: there is no CPU path to stream from
     with pytest.raises(ValueError):
         render_clip(*args, to_host=True, gather=True)
+
+
+@pytest.mark.parametrize("n,world,k", [(2949120, 8, 4), (2949120, 2, 4), (46080, 2, 3), (300, 4, 4), (131072, 8, 8), (257, 2, 1)])
+def test_reduce_scatter_pieces_tile_every_ranks_range(n, world, k):
+    """RangeScatterReducer.pieces(): the pieces of the projection backward cover chunk offsets [0, per_rank) of every
+    rank's range exactly once, in order, with non-increasing sizes (the last, un-hidden pull is the smallest)."""
+    from my_depthsplat_b200.dist import RangeScatterReducer
+    r = RangeScatterReducer.__new__(RangeScatterReducer)
+    r._N, r.world, r.num_pieces = n, world, k
+    ps = r.pieces()
+    per_rank = r._per_rank
+    assert per_rank == -(-(-(-n // 256)) // world)
+    assert 1 <= len(ps) <= k
+    pos = 0
+    for c0, cn, stride, repeat in ps:
+        assert c0 == pos and cn > 0 and stride == per_rank and repeat == world and stride >= cn
+        pos += cn
+    assert pos == per_rank
+    sizes = [p[1] for p in ps]
+    assert all(a >= b for a, b in zip(sizes[:-2], sizes[1:-1]))  # the last piece takes the remainder
+    if k >= 2 and per_rank >= 4 * k:
+        assert sizes[-1] <= sizes[0]
