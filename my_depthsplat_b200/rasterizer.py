@@ -245,6 +245,10 @@ class _SavedLease:
         if best is not None and pool[best].numel() <= 2 * nbytes + (1 << 20):
             self.tensor = pool.pop(best)
         else:
+            if nbytes > (256 << 20):
+                # a large workspace that no pooled buffer serves: the pooled ones are leftovers of smaller attempts of the same
+                # call (speculative capacities, the parts of a split) -- gigabytes that would sit next to the new buffer
+                pool.clear()
             self.tensor = torch.empty(_with_slack(nbytes, 0.05), dtype=torch.uint8, device=device)
 
     def __del__(self):
@@ -402,6 +406,7 @@ class _Rasterize(torch.autograd.Function):
                 break
             words[2 * slot] = 0
             words[2 * slot + 1] = 0
+            lease = saved = None  # the failed attempt's workspace goes back before the next one (or the parts of a split) allocate
             if overflow & 2:  # bins too long for the BINNED mode: this shape renders in GLOBAL mode from now on
                 _mode_hint[key] = _lib.SORT_GLOBAL
             if num_pairs >= _PAIR_LIMIT:
