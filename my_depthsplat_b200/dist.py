@@ -403,20 +403,15 @@ class RangeScatterReducer:
         blocks = (self._N + 255) // 256
         per_rank = (blocks + self.world - 1) // self.world
         k = self.num_pieces
-        # EVEN pieces.  Measured at N = 2 (tools/dist_timeline.py): the pulls, not the kernels, are the longer chain -- every
-        # GPU's replica crosses its NVLink once per step whatever N is (the switch reads all replicas), ~0.8 ms at the
-        # ~600 GB/s the 16-byte multimem requests reach -- so decreasing sizes (last, un-hidden pull smallest) gain nothing
-        # (5.61 against 5.60 ms), and more than four pieces lose to the tails of the shorter kernels (8: 5.60, 16: 5.82 ms
-        # against 5.55 ms)
-        weights = list(range(k, 0, -1)) if os.environ.get("B200S_PIECE_WEIGHTS", "even") == "dec" else [1] * k
-        out, c0 = [], 0
-        for j, wgt in enumerate(weights):
-            left = per_rank - c0
-            if left <= 0:
-                break
-            cn = left if j == k - 1 else min(left, max(1, -(-per_rank * wgt // sum(weights))))
-            out.append((c0, cn, per_rank, self.world))
-            c0 += cn
+        # EVEN pieces.  Measured at N = 2 (tools/dist_timeline.py, both pull kernels): decreasing sizes (the last, un-hidden
+        # pull smallest) gain nothing (5.61 against 5.60 ms with the multimem pull, 5.45 against 5.45 ms with peer loads), and
+        # more than four pieces lose to the tails of the shorter kernels (8: 5.46-5.60, 16: 5.82 ms against 5.40-5.55 ms)
+        per_piece = (per_rank + k - 1) // k
+        out = []
+        for j in range(k):
+            cn = min(per_piece, per_rank - j * per_piece)
+            if cn > 0:
+                out.append((j * per_piece, cn, per_rank, self.world))
         self._per_rank = per_rank
         return out
 
