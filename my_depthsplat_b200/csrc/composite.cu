@@ -236,17 +236,20 @@ constexpr int BWD_ROW = 33;     // padded row of the (hit, pixel) matrices
 // a quarter of the entries that pass the bounding-box cull touch no pixel that is still "alive" at that list position;
 // they are dropped before anything is stored.  All 32 lanes must call.  Branch-free below the vote: a lane the entry does
 // not reach runs the same arithmetic with alpha = 0 (T and the recurrence state come out unchanged, q = w = 0).
+// h1 = the slot's (A, B, C, opacity) quarter, hxy = its (x, y, pos, id) quarter: the caller requests them ONE HIT AHEAD (the
+// loads of hit k + 1 are in flight while hit k's dependent chain -- power, exponential, vote -- runs: 1.84 -> 1.80 ms);
+// the colour quarter is requested here, with the vote still to come (requesting it a hit ahead as well spills at 72 registers)
 template <bool DEPTH>
-__device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, PixState<DEPTH>& s, const TileGeom& g, float& q_out, float& w_out) {
-  const float4 h1 = h->q1;
-  const float dx = __fsub_rn(h->x, g.pfx), dy = __fsub_rn(h->y, g.pfy);
+__device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, const float4 h1, const float4 hxy, PixState<DEPTH>& s, const TileGeom& g,
+                                          float& q_out, float& w_out) {
+  const float4 h2 = h->q2;
+  const float dx = __fsub_rn(hxy.x, g.pfx), dy = __fsub_rn(hxy.y, g.pfy);
   const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
   const float G = exp_neg(power);  // the forward's alpha, bit for bit: the cuts fall where the forward put them
   const float araw = __fmul_rn(h1.w, G);
   const float alpha = fminf(ALPHA_MAX, araw);
-  const bool live = h->pos < s.last_contributor && power <= 0.0f && alpha >= ALPHA_MIN;
+  const bool live = __float_as_uint(hxy.z) < s.last_contributor && power <= 0.0f && alpha >= ALPHA_MIN;
   if (!__any_sync(0xffffffffu, live)) return false;
-  const float4 h2 = h->q2;
   const float a_eff = live ? alpha : 0.f;
   const float inv = rcp_approx(1.f - a_eff);  // exactly 1 for a_eff = 0
   s.T = s.T * inv;
@@ -331,10 +334,14 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel
   // one batch of nb <= 16 hits: slots[first .. first + nb)
   auto run_batch = [&](const HitSlot* batch, const int nb) {
     uint32_t nonempty = 0;
+    float4 nq1 = batch->q1, nxy = *reinterpret_cast<const float4*>(&batch->x);
 #pragma unroll 4
     for (int k = 0; k < nb; k++) {
+      const float4 cq1 = nq1, cxy = nxy;
+      const HitSlot* nx = batch + (k + 1 < nb ? k + 1 : k);
+      nq1 = nx->q1; nxy = *reinterpret_cast<const float4*>(&nx->x);
       float q, w;
-      if (!bwd_entry<DEPTH>(batch + k, s, g, q, w)) continue;
+      if (!bwd_entry<DEPTH>(batch + k, cq1, cxy, s, g, q, w)) continue;
       mq[k * BWD_ROW + lane] = q;
       mw[k * BWD_ROW + lane] = w;
       nonempty |= 1u << k;
