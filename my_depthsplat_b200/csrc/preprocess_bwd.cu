@@ -74,8 +74,12 @@ __device__ __forceinline__ void dnormvdv(const float v[3], const float dv[3], fl
 // NC = SH coefficients per channel that are ACTIVE ((deg+1)^2); NC == 0 -> colors_precomp path.
 // RAW = the scene is the encoder head's raw output (adapter.cuh): the chunk's Gaussians are rebuilt from the raw planes as
 // in the forward, and the accumulated gradients go through the adapter's chain rule before they are written.
+// Register budget: with degree-2 harmonics 47 accumulators and inputs stay live across the view loop next to the prefetched
+// records of the next view; at three CTAs per SM (80 registers) that spilled 300 bytes per thread.  Two CTAs per SM (up to
+// 128 registers, no spills to speak of) run the C2T backward in 0.577 instead of 0.646 ms -- fewer warps, but every one of
+// them keeps its loads in flight; four CTAs per SM (64 registers, 420 bytes of spills): 0.686 ms.
 template <int NC, bool MC, bool RAW = false>
-__global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_bwd_kernel(const B200sScene sc, const B200sViews vw, const B200sGradIn gin,
+__global__ void __launch_bounds__(PRE_THREADS, (NC >= 9 ? 2 : 3)) preprocess_bwd_kernel(const B200sScene sc, const B200sViews vw, const B200sGradIn gin,
                                                                      const PreBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ ViewParams s_vp[VIEW_GROUP];
