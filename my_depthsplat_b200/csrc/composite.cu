@@ -238,11 +238,12 @@ constexpr int BWD_ROW = 33;     // padded row of the (hit, pixel) matrices
 // not reach runs the same arithmetic with alpha = 0 (T and the recurrence state come out unchanged, q = w = 0).
 // h1 = the slot's (A, B, C, opacity) quarter, hxy = its (x, y, pos, id) quarter: the caller requests them ONE HIT AHEAD (the
 // loads of hit k + 1 are in flight while hit k's dependent chain -- power, exponential, vote -- runs: 1.84 -> 1.80 ms);
-// the colour quarter is requested here, with the vote still to come (requesting it a hit ahead as well spills at 72 registers)
-template <bool DEPTH>
+// Q2AHEAD: the colour quarter comes a hit ahead as well (needs the 80 registers of six CTAs per SM); otherwise it is
+// requested here, with the vote still to come
+template <bool DEPTH, bool Q2AHEAD = false>
 __device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, const float4 h1, const float4 hxy, PixState<DEPTH>& s, const TileGeom& g,
-                                          float& q_out, float& w_out) {
-  const float4 h2 = h->q2;
+                                          float& q_out, float& w_out, const float4 pre_q2 = make_float4(0.f, 0.f, 0.f, 0.f)) {
+  const float4 h2 = Q2AHEAD ? pre_q2 : h->q2;
   const float dx = __fsub_rn(hxy.x, g.pfx), dy = __fsub_rn(hxy.y, g.pfy);
   const float power = gauss_power(h1.x, h1.y, h1.z, dx, dy);
   const float G = exp_neg(power);  // the forward's alpha, bit for bit: the cuts fall where the forward put them
@@ -273,7 +274,7 @@ __device__ __forceinline__ bool bwd_entry(const HitSlot* __restrict__ h, const f
 
 // CTA_WARPS = 8: one CTA per tile; 4: two CTAs of four warps per tile (smaller scheduling units: MIN_CTAS of them fit
 // where the register file holds fewer whole tiles)
-template <bool DEPTH, int CTA_WARPS, int MIN_CTAS>
+template <bool DEPTH, int CTA_WARPS, int MIN_CTAS, bool Q2AHEAD = false>
 __global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel(const CompArgs a) {
   __shared__ HitSlot s_slot[CTA_WARPS][BWD_SLOTS];
   __shared__ float s_q[CTA_WARPS][BWD_BATCH * BWD_ROW];
@@ -334,14 +335,16 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, MIN_CTAS) composite_bwd_kernel
   // one batch of nb <= 16 hits: slots[first .. first + nb)
   auto run_batch = [&](const HitSlot* batch, const int nb) {
     uint32_t nonempty = 0;
-    float4 nq1 = batch->q1, nxy = *reinterpret_cast<const float4*>(&batch->x);
+    float4 nq1 = batch->q1, nxy = *reinterpret_cast<const float4*>(&batch->x), nq2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (Q2AHEAD) nq2 = batch->q2;
 #pragma unroll 4
     for (int k = 0; k < nb; k++) {
-      const float4 cq1 = nq1, cxy = nxy;
+      const float4 cq1 = nq1, cxy = nxy, cq2 = nq2;
       const HitSlot* nx = batch + (k + 1 < nb ? k + 1 : k);
       nq1 = nx->q1; nxy = *reinterpret_cast<const float4*>(&nx->x);
+      if (Q2AHEAD) nq2 = nx->q2;
       float q, w;
-      if (!bwd_entry<DEPTH>(batch + k, cq1, cxy, s, g, q, w)) continue;
+      if (!bwd_entry<DEPTH, Q2AHEAD>(batch + k, cq1, cxy, s, g, q, w, cq2)) continue;
       mq[k * BWD_ROW + lane] = q;
       mw[k * BWD_ROW + lane] = w;
       nonempty |= 1u << k;
@@ -449,11 +452,12 @@ cudaError_t launch_composite_bwd(const CompArgs& a, int tiles, int views, bool d
   dim3 grid(tiles, views);
   stage_mark(B200S_STAGE_COMP_BWD, stream);
   count_launches(1);
-  // Two CTAs of four warps per tile, seven per SM (72 registers, 28 KB of shared memory: 28 warps per SM; eight per SM at
-  // 64 registers measured the same: 1.92 against 1.90 ms)
   dim3 g2(tiles * 2, views);
-  if (depth) composite_bwd_kernel<true, 4, 7><<<g2, 128, 0, stream>>>(a);
-  else composite_bwd_kernel<false, 4, 7><<<g2, 128, 0, stream>>>(a);
+  // two CTAs of four warps per tile, six per SM: 80 registers hold the slot quarters of the NEXT hit (conic, position AND
+  // colour) next to the current one's -- 1.77 ms; seven per SM at 72 registers (colour quarter requested per hit, it spills
+  // otherwise): 1.80 ms; without any load ahead: 1.84 ms
+  if (depth) composite_bwd_kernel<true, 4, 6, true><<<g2, 128, 0, stream>>>(a);
+  else composite_bwd_kernel<false, 4, 6, true><<<g2, 128, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
