@@ -50,6 +50,19 @@ def test_odd_gaussian_counts_and_misaligned_scenes(n):
             assert float((got.grad.cpu() - want.grad).abs().max()) <= 2e-4 * scale
 
 
+@pytest.mark.parametrize("name,views", [("tiny", 19), ("small", 9)])
+def test_more_views_than_one_camera_group(name, views, capsys):
+    """The projection kernels load the camera blocks of a scene's views eight at a time (common.cuh VIEW_GROUP): 19 views of
+    one scene (three groups, the last one partial) and 2 scenes x 9 views (a scene's views straddle group boundaries, the
+    other scene's views in between are skipped) in ONE call, held to the strict bars of helpers.strict_parity_check: stages
+    bit-exact per view, colour + depth within 1e-5 off the fragile pixels, gradients summed over all views within 1e-4 of
+    their scale on every Gaussian that touches no flipped pixel."""
+    from helpers import strict_parity_check
+    report = strict_parity_check(make_scene(name, v_tgt=views), "depth", f"{name} x{views} views")
+    with capsys.disabled():
+        print("\n" + "\n".join(report))
+
+
 @pytest.mark.parametrize("degree", [0, 1, 2, 3])
 @pytest.mark.parametrize("layout", ["channel_major", "coeff_major"])
 def test_sh_degrees_and_layouts(degree, layout):
