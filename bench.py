@@ -559,7 +559,7 @@ def main():
                     help="N>1: sum the gradients inside the backward kernel over NVLS multicast (multimem.red) instead of one NCCL "
                          "all-reduce; measured SLOWER on B200 (one-shot multimem.red delivers every rank's data to every rank)")
     ap.add_argument("--knob", action="append", default=[], metavar="K=V",
-                    help="kernel variant switch for A/B runs (b200s_debug_set): 0 histogram, 1 sort ranking, 2 backward reduction")
+                    help="kernel variant switch for A/B runs (b200s_debug_set): 0 histogram, 1 sort ranking, 2 pull-kernel block cap, 3 peer-load flavour")
     args = ap.parse_args()
     for kv in args.knob:
         from my_depthsplat_b200 import _lib

@@ -286,9 +286,10 @@ int b200s_profile_read(float* ms_by_stage);
 /* Number of this library's kernels launched by the process so far (memsets not counted). */
 long long b200s_kernel_launches(void);
 
-/* Tuning knobs for A/B measurements (not part of the stable contract): which 0 = digit-histogram variant
- * (0 ballots, 1 MATCH.ANY, 2 shared atomics), which 1 = ranking variant (0 ballots, 1 MATCH.ANY, 2 alternating), which 2 = compositing-backward CTA shape (2: one
- * eight-warp CTA per tile instead of two four-warp ones). */
+/* Tuning knobs for A/B measurements (not part of the stable contract; a knob selects between variants with identical
+ * results): which 0 = digit-histogram variant of the GLOBAL sort (0 ballots, 1 MATCH.ANY, 2 shared atomics), which 1 = its
+ * ranking variant (0 ballots, 1 MATCH.ANY, 2 alternating), which 2 = block cap of the reduce-scatter pull kernels (0 = the
+ * default per kernel), which 3 = load flavour of the peer-load pull (0 ld.global.cg, 1 ld.relaxed.sys). */
 void b200s_debug_set(int which, int value);
 
 /* Host-memory utility (not on the data path): mapped, portable pinned memory that kernels can write
